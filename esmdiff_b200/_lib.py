@@ -1,0 +1,120 @@
+"""ctypes binding of ``libesmdiff_b200.so`` (the C ABI in ``include/esmdiff_b200.h``).
+
+There is no fallback: if the shared library is missing or no B200 is present the product path
+raises.  ``build()`` compiles the library in-tree with nvcc for sm_100a (cross-compiles without a
+GPU); the built ``.so`` is git-ignored but travels with the repo snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "lib" / "libesmdiff_b200.so"
+SRC = PKG_DIR / "csrc" / "esmdiff_b200.cu"
+HEADER = REPO_ROOT / "include" / "esmdiff_b200.h"
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+class EsmdiffError(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("n_heads", C.c_int32), ("n_layers", C.c_int32),
+                ("ffn_hidden", C.c_int32), ("n_structure_heads", C.c_int32),
+                ("seq_vocab", C.c_int32), ("struct_vocab", C.c_int32),
+                ("time_freq_dim", C.c_int32), ("time_conditioning", C.c_int32),
+                ("reserved", C.c_int32 * 7)]
+
+
+def _sources():
+    return [SRC, HEADER] + sorted((PKG_DIR / "csrc").glob("*.cuh"))
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    return any(s.stat().st_mtime > t for s in _sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> esmdiff_b200/lib/."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "nvcc")
+    LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(SRC)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise EsmdiffError(f"nvcc failed:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_P = C.c_void_p
+_SIGS = {
+    "esmdiff_abi_version": (C.c_int, []),
+    "esmdiff_last_error": (C.c_char_p, [_P]),
+    "esmdiff_create": (C.c_int, [C.POINTER(Cfg), C.c_int, C.POINTER(_P)]),
+    "esmdiff_destroy": (C.c_int, [_P]),
+    "esmdiff_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.c_int,
+                                     C.POINTER(C.c_int64), C.c_int]),
+    "esmdiff_finalize_weights": (C.c_int, [_P]),
+    "esmdiff_time_embed": (C.c_int, [_P, C.c_float, _P, _P]),
+    "esmdiff_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P]),
+    "esmdiff_forward_sigma": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "esmdiff_logits_parameterization": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "esmdiff_sample_step": (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, C.c_int, C.c_int,
+                                      C.c_uint64, C.c_uint32, _P]),
+    "esmdiff_denoise_argmax": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
+    "esmdiff_schedule": (C.c_int, [C.c_int, C.c_float, C.c_float, C.POINTER(C.c_float),
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "esmdiff_ddpm_sample": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.c_uint64, C.c_int, _P, _P]),
+    "esmdiff_ddpm_sample_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float,
+                                           C.c_uint64, C.c_int, _P]),
+    "esmdiff_synchronize": (C.c_int, [_P, _P]),
+    "esmdiff_launch_count": (C.c_int64, [_P]),
+    "esmdiff_op_gemm": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64,
+                                  _P, C.c_float, _P]),
+    "esmdiff_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "esmdiff_op_qk_norm_rope": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "esmdiff_op_attention": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "esmdiff_op_convert_bf16": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
+}
+EXPORTED = tuple(_SIGS)
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (building it first when nvcc is around and sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if needs_build():
+        try:
+            build()
+        except (EsmdiffError, FileNotFoundError) as e:
+            if not LIB_PATH.exists():
+                raise EsmdiffError(
+                    f"{LIB_PATH} is missing and could not be built ({e}); esmdiff_b200 has no "
+                    "fallback path -- run __graft_entry__.build() where nvcc is available") from e
+    L = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(L, name)          # AttributeError if the .so does not export it
+        fn.restype, fn.argtypes = res, args
+    if L.esmdiff_abi_version() != 1:
+        raise EsmdiffError("ABI version mismatch between _lib.py and libesmdiff_b200.so")
+    _lib = L
+    return L

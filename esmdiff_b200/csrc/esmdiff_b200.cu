@@ -1,0 +1,750 @@
+// esmdiff_b200: context, weights, forward orchestration and the C ABI (include/esmdiff_b200.h).
+// Unity build: all kernels are included here so the library is one translation unit.
+#include "../../include/esmdiff_b200.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <set>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include "sampler.cuh"
+
+using namespace esmdiff;
+typedef __nv_bfloat16 bf16;
+
+static std::string g_create_error;
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            return c->fail(std::string(#call) + ": " + cudaGetErrorString(e_));                \
+        }                                                                                      \
+    } while (0)
+
+struct LayerW {
+    float *ln1_w = nullptr, *ln1_b = nullptr, *qln_w = nullptr, *kln_w = nullptr;
+    float *ln2_w = nullptr, *ln2_b = nullptr;
+    bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct esmdiff_ctx {
+    esmdiff_cfg cfg;
+    int device = 0;
+    int num_sms = 148;
+    std::string err;
+    int64_t launches = 0;
+    EncodeTiledFn encode = nullptr;
+
+    std::vector<LayerW> layers;
+    float *seq_embed = nullptr, *struct_embed = nullptr, *plddt_w = nullptr, *plddt_b = nullptr;
+    float *res_w = nullptr, *res_b = nullptr, *ss8 = nullptr, *sasa = nullptr, *const_vec = nullptr;
+    float *norm_w = nullptr, *h0_b = nullptr, *h2_w = nullptr, *h2_b = nullptr, *h3_b = nullptr;
+    bf16 *h0_w = nullptr, *h3_w = nullptr;
+    float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
+    std::set<std::string> loaded;
+    bool finalized = false;
+    std::vector<void*> owned;
+
+    // workspace (grows with the largest B*T seen)
+    int64_t ws_rows = 0;
+    float *x = nullptr, *headh = nullptr, *logits_ws = nullptr;
+    bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;
+    float *cond = nullptr, *te_hidden = nullptr, *inv_freq = nullptr;
+    float *cos_t = nullptr, *sin_t = nullptr;
+    int rope_T = 0;
+    int* dev_err = nullptr;
+    int64_t *x_tok = nullptr, *seq_tok = nullptr;     // staging for the *_host entry point
+    int64_t tok_rows = 0;
+
+    std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> tmaps;
+
+    int fail(const std::string& m) {
+        err = m;
+        return 1;
+    }
+    template <typename T>
+    int alloc(T** p, size_t n) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+        if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        owned.push_back(q);
+        *p = reinterpret_cast<T*>(q);
+        return 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors: bf16 row-major [rows, cols] (cols contiguous), box [box_rows][64 cols], 128B swizzle
+// ------------------------------------------------------------------------------------------------
+static int get_tmap(esmdiff_ctx* c, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                    uint32_t box_rows, CUtensorMap* out) {
+    auto key = std::make_tuple(base, rows, cols * 1000003ull + ld_elems, box_rows, 64u);
+    auto it = c->tmaps.find(key);
+    if (it != c->tmaps.end()) {
+        *out = it->second;
+        return 0;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld_elems * sizeof(bf16)};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tm;
+    CUresult r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
+                           gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
+                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+        return c->fail(buf);
+    }
+    if (c->tmaps.size() > 4096) c->tmaps.clear();
+    c->tmaps[key] = tm;
+    *out = tm;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launchers
+// ------------------------------------------------------------------------------------------------
+static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, int M, int N, int K,
+                       void* out, int64_t ldo, const float* bias, float scale, cudaStream_t st) {
+    if (K % gemm::BK != 0 || K <= 0) return c->fail("gemm: K must be a positive multiple of 64");
+    if (epi == gemm::EPI_SWIGLU_BF16 && N % gemm::BN != 0)
+        return c->fail("gemm: SwiGLU epilogue needs N % 256 == 0");
+    CUtensorMap ta, tb;
+    if (get_tmap(c, A, M, K, K, gemm::BM, &ta)) return 1;
+    if (get_tmap(c, W, N, K, K, gemm::BN, &tb)) return 1;
+    gemm::Params p;
+    p.M = M; p.N = N; p.K = K;
+    p.m_tiles = (M + gemm::BM - 1) / gemm::BM;
+    p.n_tiles = (N + gemm::BN - 1) / gemm::BN;
+    p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+#define LAUNCH_GEMM(E)                                                                         \
+    case E: {                                                                                  \
+        static bool attr_set = false;                                                          \
+        if (!attr_set) {                                                                       \
+            CK(cudaFuncSetAttribute(gemm::gemm_bf16_tn_kernel<E>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES)); \
+            attr_set = true;                                                                   \
+        }                                                                                      \
+        gemm::gemm_bf16_tn_kernel<E><<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p); \
+        break;                                                                                 \
+    }
+    switch (epi) {
+        LAUNCH_GEMM(gemm::EPI_STORE_BF16)
+        LAUNCH_GEMM(gemm::EPI_RESID_F32)
+        LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16)
+        LAUNCH_GEMM(gemm::EPI_BIAS_GELU_F32)
+        LAUNCH_GEMM(gemm::EPI_BIAS_F32)
+        default: return c->fail("gemm: unknown epilogue");
+    }
+#undef LAUNCH_GEMM
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_layernorm(esmdiff_ctx* c, const float* x, const float* w, const float* b, bf16* y,
+                            int M, int D, cudaStream_t st) {
+    if (D % 128 != 0 || D > 128 * 12) return c->fail("layernorm: D must be a multiple of 128, <= 1536");
+    const int grid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    ew::layernorm_f32_to_bf16_kernel<12><<<grid, ew::ROWS_PER_BLOCK * 32, 0, st>>>(x, w, b, y, M, D, 1e-5f);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_rope(esmdiff_ctx* c, int T, cudaStream_t st) {
+    if (T <= c->rope_T) return 0;
+    if (!c->inv_freq) {
+        float h[32];
+        for (int i = 0; i < 32; ++i) h[i] = 1.0f / powf(10000.0f, static_cast<float>(2 * i) / 64.0f);
+        if (c->alloc(&c->inv_freq, 32)) return 1;
+        CK(cudaMemcpy(c->inv_freq, h, sizeof h, cudaMemcpyHostToDevice));
+    }
+    int cap = 1056;
+    while (cap < T) cap *= 2;
+    if (c->alloc(&c->cos_t, (size_t)cap * 32)) return 1;     // old tables stay owned until destroy
+    if (c->alloc(&c->sin_t, (size_t)cap * 32)) return 1;
+    ew::rope_table_kernel<<<(cap * 32 + 255) / 256, 256, 0, st>>>(c->inv_freq, c->cos_t, c->sin_t, cap);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->rope_T = cap;
+    return 0;
+}
+
+static int launch_qk_norm_rope(esmdiff_ctx* c, bf16* qkv, const float* qw, const float* kw, int M, int T,
+                               int D, cudaStream_t st) {
+    if (D % 256 != 0 || D > 256 * 6) return c->fail("qk_norm_rope: D must be a multiple of 256, <= 1536");
+    if (ensure_rope(c, T, st)) return 1;
+    const int grid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    ew::qk_layernorm_rope_kernel<6><<<grid, ew::ROWS_PER_BLOCK * 32, 0, st>>>(qkv, qw, kw, c->cos_t,
+                                                                               c->sin_t, M, D, T, 1e-5f);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H, cudaStream_t st) {
+    const int D = H * attn::DH;
+    const int64_t M = (int64_t)B * T;
+    CUtensorMap tq, tkv;
+    if (get_tmap(c, qkv, M, 3 * D, 3 * D, attn::BQ, &tq)) return 1;
+    if (get_tmap(c, qkv, M, 3 * D, 3 * D, attn::BKV, &tkv)) return 1;
+    attn::Params p;
+    p.B = B; p.T = T; p.H = H;
+    p.q_tiles = (T + attn::BQ - 1) / attn::BQ;
+    p.ctx = out;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CK(cudaFuncSetAttribute(attn::attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                attn::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = B * H * p.q_tiles;
+    attn::attention_fwd_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tq, tkv, p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int launch_time_embed(esmdiff_ctx* c, float sigma, float* cond, cudaStream_t st) {
+    const int D = c->cfg.d_model;
+    if (!c->cfg.time_conditioning) sigma = 0.f;           // model.py:538-539
+    ew::time_embed_hidden_kernel<<<(D + 7) / 8, 256, 0, st>>>(sigma, c->te_w0, c->te_b0, c->te_hidden, D,
+                                                              c->cfg.time_freq_dim);
+    ew::time_embed_out_kernel<<<(D + 7) / 8, 256, 0, st>>>(c->te_hidden, c->te_w2, c->te_b2, cond, D);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
+    if (M <= c->ws_rows) return 0;
+    // free the previous workspace buffers
+    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf};
+    for (void* o : olds)
+        if (o) {
+            cudaFree(o);
+            for (auto& q : c->owned)
+                if (q == o) q = nullptr;
+        }
+    c->tmaps.clear();
+    const int64_t D = c->cfg.d_model, F = c->cfg.ffn_hidden, V = c->cfg.n_structure_heads;
+    c->x = nullptr; c->headh = nullptr; c->logits_ws = nullptr;
+    c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr;
+    if (c->alloc(&c->x, M * D)) return 1;
+    if (c->alloc(&c->headh, M * D)) return 1;
+    if (c->alloc(&c->logits_ws, M * V)) return 1;
+    if (c->alloc(&c->xn, M * D)) return 1;
+    if (c->alloc(&c->qkv, M * 3 * D)) return 1;
+    if (c->alloc(&c->att, M * D)) return 1;
+    if (c->alloc(&c->hbuf, M * F)) return 1;
+    c->ws_rows = M;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T,
+                        const float* aux, int64_t aux_stride, float* logits, float* emb_out,
+                        cudaStream_t st) {
+    if (!c->finalized) return c->fail("forward: esmdiff_finalize_weights has not succeeded");
+    if (B <= 0 || T <= 0) return c->fail("forward: B and T must be positive");
+    const int64_t M64 = (int64_t)B * T;
+    if (M64 > (1ll << 30)) return c->fail("forward: B*T too large");
+    const int M = (int)M64;
+    const int D = c->cfg.d_model, F = c->cfg.ffn_hidden, H = c->cfg.n_heads, V = c->cfg.n_structure_heads;
+    if (ensure_workspace(c, M)) return 1;
+    const float rs = sqrtf((float)c->cfg.n_layers / 36.0f);
+
+    const int rgrid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    ew::embed_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const long long*>(seq),
+                                            reinterpret_cast<const long long*>(xt), c->seq_embed,
+                                            c->struct_embed, c->const_vec, aux, aux_stride, c->x, M, D,
+                                            c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err);
+    c->launches++;
+    CK(cudaGetLastError());
+
+    for (int l = 0; l < c->cfg.n_layers; ++l) {
+        const LayerW& w = c->layers[l];
+        if (launch_layernorm(c, c->x, w.ln1_w, w.ln1_b, c->xn, M, D, st)) return 1;
+        if (launch_gemm(c, gemm::EPI_STORE_BF16, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, nullptr, 1.f, st)) return 1;
+        if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
+        if (launch_attention(c, c->qkv, c->att, B, T, H, st)) return 1;
+        if (launch_gemm(c, gemm::EPI_RESID_F32, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st)) return 1;
+        // block 0's geometric attention contributes exactly 0 on this path
+        if (launch_layernorm(c, c->x, w.ln2_w, w.ln2_b, c->xn, M, D, st)) return 1;
+        if (launch_gemm(c, gemm::EPI_SWIGLU_BF16, c->xn, w.w1, M, 2 * F, D, c->hbuf, F, nullptr, 1.f, st)) return 1;
+        if (launch_gemm(c, gemm::EPI_RESID_F32, c->hbuf, w.w2, M, D, F, c->x, D, nullptr, rs, st)) return 1;
+    }
+    if (emb_out) CK(cudaMemcpyAsync(emb_out, c->x, (size_t)M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (launch_layernorm(c, c->x, c->norm_w, nullptr, c->xn, M, D, st)) return 1;
+    if (launch_gemm(c, gemm::EPI_BIAS_GELU_F32, c->xn, c->h0_w, M, D, D, c->headh, D, c->h0_b, 1.f, st)) return 1;
+    if (launch_layernorm(c, c->headh, c->h2_w, c->h2_b, c->xn, M, D, st)) return 1;
+    if (launch_gemm(c, gemm::EPI_BIAS_F32, c->xn, c->h3_w, M, V, D, logits, V, c->h3_b, 1.f, st)) return 1;
+    return 0;
+}
+
+template <int MODE>
+static int launch_sampler(esmdiff_ctx* c, const float* logits, const float* u, int64_t* x, float* logp,
+                          int M, float mc_t, float mc_s, uint64_t seed, uint32_t step, cudaStream_t st) {
+    const int V = c->cfg.n_structure_heads;
+    if (V > sampler::THREADS * sampler::MAX_PER_THREAD) return c->fail("sampler: vocabulary too large");
+    sampler::sample_rows_kernel<MODE><<<M, sampler::THREADS, 0, st>>>(
+        logits, (long long)V, u, reinterpret_cast<long long*>(x), logp, M, V,
+        ESMDIFF_STRUCTURE_MASK_TOKEN, mc_t, mc_s, (unsigned long long)seed, step);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void bf16_to_f32_kernel(const bf16* s, float* d, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = __bfloat162float(s[i]);
+}
+enum Kind { K_F32, K_BF16, K_BF16_SWIGLU, K_SKIP };
+struct Slot {
+    Kind kind;
+    void** dst;
+    std::vector<int64_t> shape;
+};
+}  // namespace
+
+static bool resolve_key(esmdiff_ctx* c, const std::string& key, Slot* s) {
+    const int64_t D = c->cfg.d_model, F = c->cfg.ffn_hidden, V = c->cfg.n_structure_heads;
+    auto f32 = [&](float** p, std::vector<int64_t> shp) { *s = {K_F32, (void**)p, shp}; return true; };
+    auto b16 = [&](bf16** p, std::vector<int64_t> shp) { *s = {K_BF16, (void**)p, shp}; return true; };
+    auto skip = [&]() { *s = {K_SKIP, nullptr, {}}; return true; };
+    if (key.rfind("sigma_embedder.mlp.", 0) == 0) {
+        const std::string r = key.substr(19);
+        if (r == "0.weight") return f32(&c->te_w0, {D, c->cfg.time_freq_dim});
+        if (r == "0.bias") return f32(&c->te_b0, {D});
+        if (r == "2.weight") return f32(&c->te_w2, {D, D});
+        if (r == "2.bias") return f32(&c->te_b2, {D});
+        return false;
+    }
+    if (key.rfind("net.", 0) != 0) return false;
+    const std::string k = key.substr(4);
+    if (k == "encoder.sequence_embed.weight") return f32(&c->seq_embed, {c->cfg.seq_vocab, D});
+    if (k == "encoder.structure_tokens_embed.weight") return f32(&c->struct_embed, {c->cfg.struct_vocab, D});
+    if (k == "encoder.plddt_projection.weight") return f32(&c->plddt_w, {D, 16});
+    if (k == "encoder.plddt_projection.bias") return f32(&c->plddt_b, {D});
+    if (k == "encoder.structure_per_res_plddt_projection.weight") return f32(&c->res_w, {D, 16});
+    if (k == "encoder.structure_per_res_plddt_projection.bias") return f32(&c->res_b, {D});
+    if (k == "encoder.ss8_embed.weight") return f32(&c->ss8, {11, D});
+    if (k == "encoder.sasa_embed.weight") return f32(&c->sasa, {19, D});
+    if (k.rfind("encoder.function_embed.", 0) == 0 || k == "encoder.residue_embed.weight") return skip();
+    if (k == "transformer.norm.weight") return f32(&c->norm_w, {D});
+    if (k.rfind("output_heads.structure_head.", 0) == 0) {
+        const std::string r = k.substr(28);
+        if (r == "0.weight") return b16(&c->h0_w, {D, D});
+        if (r == "0.bias") return f32(&c->h0_b, {D});
+        if (r == "2.weight") return f32(&c->h2_w, {D});
+        if (r == "2.bias") return f32(&c->h2_b, {D});
+        if (r == "3.weight") return b16(&c->h3_w, {V, D});
+        if (r == "3.bias") return f32(&c->h3_b, {V});
+        return false;
+    }
+    if (k.rfind("output_heads.", 0) == 0) return skip();      // other ESM3 heads: not on this path
+    if (k.rfind("transformer.blocks.", 0) == 0) {
+        const size_t dot = k.find('.', 19);
+        if (dot == std::string::npos) return false;
+        const int l = atoi(k.substr(19, dot - 19).c_str());
+        if (l < 0 || l >= c->cfg.n_layers) return false;
+        LayerW& w = c->layers[l];
+        const std::string r = k.substr(dot + 1);
+        if (r.rfind("geom_attn.", 0) == 0) return skip();      // exact zero on this path (A6)
+        if (r == "attn.layernorm_qkv.0.weight") return f32(&w.ln1_w, {D});
+        if (r == "attn.layernorm_qkv.0.bias") return f32(&w.ln1_b, {D});
+        if (r == "attn.layernorm_qkv.1.weight") return b16(&w.wqkv, {3 * D, D});
+        if (r == "attn.q_ln.weight") return f32(&w.qln_w, {D});
+        if (r == "attn.k_ln.weight") return f32(&w.kln_w, {D});
+        if (r == "attn.out_proj.weight") return b16(&w.wo, {D, D});
+        if (r == "ffn.0.weight") return f32(&w.ln2_w, {D});
+        if (r == "ffn.0.bias") return f32(&w.ln2_b, {D});
+        if (r == "ffn.1.weight") { *s = {K_BF16_SWIGLU, (void**)&w.w1, {2 * F, D}}; return true; }
+        if (r == "ffn.3.weight") return b16(&w.w2, {D, F});
+        return false;
+    }
+    return false;
+}
+
+static std::vector<std::string> required_keys(const esmdiff_ctx* c) {
+    std::vector<std::string> k = {
+        "net.encoder.sequence_embed.weight", "net.encoder.structure_tokens_embed.weight",
+        "net.encoder.plddt_projection.weight", "net.encoder.plddt_projection.bias",
+        "net.encoder.structure_per_res_plddt_projection.weight",
+        "net.encoder.structure_per_res_plddt_projection.bias", "net.encoder.ss8_embed.weight",
+        "net.encoder.sasa_embed.weight", "net.transformer.norm.weight",
+        "net.output_heads.structure_head.0.weight", "net.output_heads.structure_head.0.bias",
+        "net.output_heads.structure_head.2.weight", "net.output_heads.structure_head.2.bias",
+        "net.output_heads.structure_head.3.weight", "net.output_heads.structure_head.3.bias",
+        "sigma_embedder.mlp.0.weight", "sigma_embedder.mlp.0.bias", "sigma_embedder.mlp.2.weight",
+        "sigma_embedder.mlp.2.bias"};
+    const char* per[] = {"attn.layernorm_qkv.0.weight", "attn.layernorm_qkv.0.bias",
+                         "attn.layernorm_qkv.1.weight", "attn.q_ln.weight", "attn.k_ln.weight",
+                         "attn.out_proj.weight", "ffn.0.weight", "ffn.0.bias", "ffn.1.weight",
+                         "ffn.3.weight"};
+    for (int l = 0; l < c->cfg.n_layers; ++l)
+        for (const char* r : per) k.push_back("net.transformer.blocks." + std::to_string(l) + "." + r);
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int esmdiff_abi_version(void) { return ESMDIFF_ABI_VERSION; }
+
+const char* esmdiff_last_error(const esmdiff_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
+    if (!cfg || !out) { g_create_error = "create: null argument"; return 1; }
+    *out = nullptr;
+    if (cfg->d_model <= 0 || cfg->d_model % 256 != 0 || cfg->d_model > 1536 ||
+        cfg->n_heads * 64 != cfg->d_model || cfg->n_layers <= 0 || cfg->ffn_hidden % 128 != 0 ||
+        cfg->ffn_hidden <= 0 || cfg->n_structure_heads <= ESMDIFF_STRUCTURE_MASK_TOKEN ||
+        cfg->n_structure_heads > 4352 || cfg->time_freq_dim <= 0 || cfg->time_freq_dim % 2 != 0) {
+        g_create_error = "create: unsupported dimensions (need d_model % 256 == 0 <= 1536, d_head 64, "
+                         "ffn_hidden % 128 == 0, 4096 < n_structure_heads <= 4352)";
+        return 1;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("create: no CUDA device (") + cudaGetErrorString(e) +
+                         "); esmdiff_b200 has no CPU fallback";
+        return 2;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "create: bad device index"; return 1; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        g_create_error = "create: device is not sm_100 (Blackwell B200); kernels are sm_100a only";
+        return 2;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return 1; }
+    esmdiff_ctx* c = new esmdiff_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->layers.resize(cfg->n_layers);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn) {
+        g_create_error = "create: cuTensorMapEncodeTiled not available from the driver";
+        delete c;
+        return 1;
+    }
+    c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    if (c->alloc(&c->dev_err, 1) || c->alloc(&c->cond, cfg->d_model) || c->alloc(&c->te_hidden, cfg->d_model) ||
+        c->alloc(&c->const_vec, cfg->d_model)) {
+        g_create_error = c->err;
+        delete c;
+        return 1;
+    }
+    cudaMemset(c->dev_err, 0, sizeof(int));
+    int zero = 0;
+    cudaMemcpyToSymbol(g_abort_flag, &zero, sizeof(int));
+    *out = c;
+    return 0;
+}
+
+int esmdiff_destroy(esmdiff_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->owned)
+        if (p) cudaFree(p);
+    delete c;
+    return 0;
+}
+
+int esmdiff_set_weight(esmdiff_ctx* c, const char* key, const void* data, int on_device, int dtype,
+                       const int64_t* shape, int ndim) {
+    if (!c || !key || !data) return 1;
+    CK(cudaSetDevice(c->device));
+    Slot s;
+    if (!resolve_key(c, key, &s)) return c->fail(std::string("set_weight: unexpected key ") + key);
+    if (s.kind == K_SKIP) return 0;
+    if ((int)s.shape.size() != ndim) return c->fail(std::string("set_weight: rank mismatch for ") + key);
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) {
+        if (shape[i] != s.shape[i]) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "set_weight: size mismatch for %s: dim %d is %lld, expected %lld", key, i,
+                     (long long)shape[i], (long long)s.shape[i]);
+            return c->fail(buf);
+        }
+        n *= shape[i];
+    }
+    if (dtype != ESMDIFF_F32 && dtype != ESMDIFF_BF16) return c->fail("set_weight: dtype must be f32 or bf16");
+    // stage as fp32 on the device
+    float* stage = nullptr;
+    CK(cudaMalloc(&stage, n * sizeof(float)));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (dtype == ESMDIFF_F32) {
+        CK(cudaMemcpy(stage, data, n * sizeof(float), kind));
+    } else {
+        bf16* tmp = nullptr;
+        CK(cudaMalloc(&tmp, n * sizeof(bf16)));
+        CK(cudaMemcpy(tmp, data, n * sizeof(bf16), kind));
+        bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256>>>(tmp, stage, n);
+        CK(cudaDeviceSynchronize());
+        cudaFree(tmp);
+    }
+    if (*s.dst == nullptr) {
+        void* q = nullptr;
+        const size_t bytes = n * (s.kind == K_F32 ? sizeof(float) : sizeof(bf16));
+        cudaError_t e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) { cudaFree(stage); return c->fail("set_weight: out of device memory"); }
+        c->owned.push_back(q);
+        *s.dst = q;
+    }
+    if (s.kind == K_F32) {
+        CK(cudaMemcpy(*s.dst, stage, n * sizeof(float), cudaMemcpyDeviceToDevice));
+    } else {
+        const int64_t rows = s.shape[0], cols = s.shape[1];
+        ew::convert_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256>>>(
+            stage, reinterpret_cast<bf16*>(*s.dst), rows, cols, s.kind == K_BF16_SWIGLU ? c->cfg.ffn_hidden : 0);
+        CK(cudaGetLastError());
+    }
+    CK(cudaDeviceSynchronize());
+    cudaFree(stage);
+    c->loaded.insert(key);
+    c->finalized = false;
+    return 0;
+}
+
+int esmdiff_finalize_weights(esmdiff_ctx* c) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    std::string missing;
+    int nmiss = 0;
+    for (const std::string& k : required_keys(c))
+        if (!c->loaded.count(k)) {
+            if (nmiss < 8) missing += (nmiss ? ", " : "") + k;
+            ++nmiss;
+        }
+    if (nmiss) {
+        return c->fail("finalize_weights: Missing key(s) in state_dict: " + missing +
+                       (nmiss > 8 ? " ... (" + std::to_string(nmiss) + " total)" : ""));
+    }
+    const int D = c->cfg.d_model;
+    ew::default_tracks_kernel<<<(D + 127) / 128, 128>>>(c->plddt_w, c->plddt_b, c->res_w, c->res_b, c->ss8,
+                                                        c->sasa, c->const_vec, D);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    c->finalized = true;
+    return 0;
+}
+
+int esmdiff_time_embed(esmdiff_ctx* c, float sigma, float* cond_out, void* stream) {
+    if (!c || !c->finalized) return c ? c->fail("time_embed: weights not finalized") : 1;
+    CK(cudaSetDevice(c->device));
+    return launch_time_embed(c, sigma, cond_out, (cudaStream_t)stream);
+}
+
+int esmdiff_forward(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T, const float* aux,
+                    int64_t aux_row_stride, float* logits, float* emb, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return forward_impl(c, seq, xt, B, T, aux, aux_row_stride, logits, emb, (cudaStream_t)stream);
+}
+
+int esmdiff_forward_sigma(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T, float sigma,
+                          float* logits, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    if (!c->finalized) return c->fail("forward: esmdiff_finalize_weights has not succeeded");
+    if (launch_time_embed(c, sigma, c->cond, (cudaStream_t)stream)) return 1;
+    return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, (cudaStream_t)stream);
+}
+
+int esmdiff_logits_parameterization(esmdiff_ctx* c, const float* logits, const int64_t* xt, int B, int T,
+                                    float* logp, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_sampler<2>(c, logits, nullptr, const_cast<int64_t*>(xt), logp, B * T, 0.f, 0.f, 0, 0,
+                             (cudaStream_t)stream);
+}
+
+int esmdiff_sample_step(esmdiff_ctx* c, int64_t* x, const float* logits, const float* u, float mc_t, float mc_s,
+                        int B, int T, uint64_t seed, uint32_t step, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_sampler<0>(c, logits, u, x, nullptr, B * T, mc_t, mc_s, seed, step, (cudaStream_t)stream);
+}
+
+int esmdiff_denoise_argmax(esmdiff_ctx* c, int64_t* x, const float* logits, int B, int T, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_sampler<1>(c, logits, nullptr, x, nullptr, B * T, 0.f, 0.f, 0, 0, (cudaStream_t)stream);
+}
+
+int esmdiff_schedule(int steps, float eps, float noise_eps, float* sigma, float* mc_t, float* mc_s) {
+    if (steps <= 0 || !sigma || !mc_t || !mc_s) return 1;
+    // torch.linspace(1, eps, steps+1) in fp32: symmetric fill from both ends
+    const int n = steps + 1;
+    const float start = 1.0f, end = eps;
+    const float stepv = (end - start) / static_cast<float>(n - 1);
+    const float dt = static_cast<float>((1.0 - static_cast<double>(eps)) / steps);
+    const float one_m = 1.0f - noise_eps;
+    for (int i = 0; i < n; ++i) {
+        const float t = i < n / 2 ? start + stepv * i : end - stepv * (n - 1 - i);
+        sigma[i] = -log1pf(-one_m * t);
+        if (i < steps) {
+            mc_t[i] = 1.0f - expf(-sigma[i]);
+            const float ts = t - dt;
+            mc_s[i] = 1.0f - expf(log1pf(-one_m * ts));
+        }
+    }
+    return 0;
+}
+
+int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior, int B, int T, int steps,
+                        const float* sigma, const float* mc_t, const float* mc_s, uint64_t seed,
+                        int noise_removal, int64_t* out, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    if (!c->finalized) return c->fail("ddpm_sample: esmdiff_finalize_weights has not succeeded");
+    if (steps <= 0 || !sigma || !mc_t || !mc_s) return c->fail("ddpm_sample: bad schedule");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = B * T;
+    if (ensure_workspace(c, M)) return 1;
+    if (prior) {
+        CK(cudaMemcpyAsync(out, prior, (size_t)M * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    } else {
+        std::vector<int64_t> h((size_t)M, (int64_t)ESMDIFF_STRUCTURE_MASK_TOKEN);
+        CK(cudaMemcpyAsync(out, h.data(), (size_t)M * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    for (int i = 0; i < steps; ++i) {
+        if (launch_time_embed(c, sigma[i], c->cond, st)) return 1;
+        if (forward_impl(c, seq, out, B, T, c->cond, 0, c->logits_ws, nullptr, st)) return 1;
+        if (launch_sampler<0>(c, c->logits_ws, nullptr, out, nullptr, M, mc_t[i], mc_s[i], seed, (uint32_t)i, st))
+            return 1;
+    }
+    if (noise_removal) {
+        if (launch_time_embed(c, sigma[steps], c->cond, st)) return 1;
+        if (forward_impl(c, seq, out, B, T, c->cond, 0, c->logits_ws, nullptr, st)) return 1;
+        if (launch_sampler<1>(c, c->logits_ws, nullptr, out, nullptr, M, 0.f, 0.f, 0, 0, st)) return 1;
+    }
+    return 0;
+}
+
+int esmdiff_synchronize(esmdiff_ctx* c, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaGetLastError());
+    int abort_flag = 0, tok_err = 0;
+    CK(cudaMemcpyFromSymbol(&abort_flag, g_abort_flag, sizeof(int)));
+    CK(cudaMemcpy(&tok_err, c->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (abort_flag) {
+        int zero = 0;
+        cudaMemcpyToSymbol(g_abort_flag, &zero, sizeof(int));
+        return c->fail("pipeline watchdog: an mbarrier wait timed out inside a tcgen05 kernel");
+    }
+    if (tok_err) {
+        cudaMemset(c->dev_err, 0, sizeof(int));
+        return c->fail("IndexError: token id out of range in embedding lookup");
+    }
+    return 0;
+}
+
+int esmdiff_ddpm_sample_host(esmdiff_ctx* c, const int64_t* seq_host, const int64_t* prior_host, int B, int T,
+                             int steps, float eps, uint64_t seed, int noise_removal, int64_t* out_host) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    const int64_t M = (int64_t)B * T;
+    if (M > c->tok_rows) {
+        if (c->alloc(&c->x_tok, 2 * M)) return 1;
+        if (c->alloc(&c->seq_tok, M)) return 1;
+        c->tok_rows = M;
+    }
+    std::vector<float> sg(steps + 1), a(steps), b(steps);
+    if (esmdiff_schedule(steps, eps, 1e-3f, sg.data(), a.data(), b.data())) return c->fail("bad schedule");
+    cudaStream_t st = 0;
+    CK(cudaMemcpyAsync(c->seq_tok, seq_host, M * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    int64_t* prior_dev = nullptr;
+    if (prior_host) {
+        prior_dev = c->x_tok + M;
+        CK(cudaMemcpyAsync(prior_dev, prior_host, M * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    }
+    if (esmdiff_ddpm_sample(c, c->seq_tok, prior_dev, B, T, steps, sg.data(), a.data(), b.data(), seed,
+                            noise_removal, c->x_tok, st))
+        return 1;
+    CK(cudaMemcpyAsync(out_host, c->x_tok, M * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    return esmdiff_synchronize(c, st);
+}
+
+int64_t esmdiff_launch_count(const esmdiff_ctx* c) { return c ? c->launches : 0; }
+
+int esmdiff_op_gemm(esmdiff_ctx* c, int epi, const void* a, const void* w, int M, int N, int K, void* out,
+                    int64_t ldo, const float* bias, float scale, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_gemm(c, epi, (const bf16*)a, (const bf16*)w, M, N, K, out, ldo, bias, scale, (cudaStream_t)stream);
+}
+int esmdiff_op_layernorm(esmdiff_ctx* c, const float* x, const float* w, const float* b, void* y, int M, int D,
+                         void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_layernorm(c, x, w, b, (bf16*)y, M, D, (cudaStream_t)stream);
+}
+int esmdiff_op_qk_norm_rope(esmdiff_ctx* c, void* qkv, const float* qw, const float* kw, int B, int T, int D,
+                            void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_qk_norm_rope(c, (bf16*)qkv, qw, kw, B * T, T, D, (cudaStream_t)stream);
+}
+int esmdiff_op_attention(esmdiff_ctx* c, const void* qkv, void* out, int B, int T, int H, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_attention(c, (const bf16*)qkv, (bf16*)out, B, T, H, (cudaStream_t)stream);
+}
+int esmdiff_op_convert_bf16(esmdiff_ctx* c, const float* src, void* dst, int64_t rows, int64_t cols,
+                            int swiglu_hidden, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = rows * cols;
+    ew::convert_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        src, (bf16*)dst, rows, cols, swiglu_hidden);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+/* esmdiff_b200 -- C ABI of the B200-native ESMDiff ddpm sampling path.
+ *
+ * The reference (lujiarui/esmdiff) is pure Python: it has no FFI.  The boundary this library
+ * stands behind is three Python call sites; each entry point below names the
+ * reference interface it replaces.  Plain pointers and sizes only -- no torch types.
+ *
+ *   - All `*_dev` pointers are device pointers on the context's device; the library borrows
+ *     them for the duration of the (stream-ordered, asynchronous) call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Every function returns 0 on success, non-zero on failure; esmdiff_last_error() gives text.
+ *   - One context per device; not thread-safe; calls are ordered on the given stream.
+ *   - There is no CPU fallback: on a machine without a CUDA device esmdiff_create() fails.
+ */
+#ifndef ESMDIFF_B200_H
+#define ESMDIFF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESMDIFF_ABI_VERSION 1
+
+#define ESMDIFF_STRUCTURE_MASK_TOKEN 4096 /* esm.utils.constants.esm3.STRUCTURE_MASK_TOKEN; model.py:381 */
+
+typedef struct esmdiff_ctx esmdiff_ctx;
+
+/* Hyper-parameters: CustomizedESM3.__init__ (slm/models/net.py:323-334), configs/experiment/mdlm.yaml:26-58 */
+typedef struct esmdiff_cfg {
+    int32_t d_model;            /* 1536 */
+    int32_t n_heads;            /* 24   (d_head must be 64) */
+    int32_t n_layers;           /* 48   (residual scale = sqrt(n_layers / 36)) */
+    int32_t ffn_hidden;         /* 4096 = ceil(8/3 d / 256) * 256 */
+    int32_t n_structure_heads;  /* 4101 */
+    int32_t seq_vocab;          /* 64 */
+    int32_t struct_vocab;       /* 4101 */
+    int32_t time_freq_dim;      /* 256, TimestepEmbedder.frequency_embedding_size (net.py:487) */
+    int32_t time_conditioning;  /* mdlm.yaml:40; 0 -> sigma is zeroed (model.py:538-539) */
+    int32_t reserved[7];
+} esmdiff_cfg;
+
+enum esmdiff_dtype { ESMDIFF_F32 = 0, ESMDIFF_BF16 = 1 };
+
+int esmdiff_abi_version(void);
+const char* esmdiff_last_error(const esmdiff_ctx* ctx); /* ctx may be NULL: last create() error */
+
+/* Replaces hydra.utils.instantiate(cfg.model) + .to(device) (slm/utils/checkpoint_utils.py:59,72). */
+int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out);
+int esmdiff_destroy(esmdiff_ctx* ctx);
+
+/* Replaces model.load_state_dict(all_params) (checkpoint_utils.py:63-64).  `key` is the state-dict
+ * key of the DeepSpeed ['module'] dict ("net.transformer.blocks.0.attn.out_proj.weight",
+ * "sigma_embedder.mlp.0.bias", ...).  Data is copied (and converted: GEMM weights are kept in
+ * bf16, FFN W1 rows are interleaved gate/up per 128).  Keys the ddpm path never reads
+ * (function/residue embeddings, geom_attn.*) are accepted and dropped.  Unknown keys fail. */
+int esmdiff_set_weight(esmdiff_ctx* ctx, const char* key, const void* data, int on_device,
+                       int dtype, const int64_t* shape, int ndim);
+/* Strict check that every key of the path has been set; builds derived constants. */
+int esmdiff_finalize_weights(esmdiff_ctx* ctx);
+
+/* Replaces sigma_embedder(sigma) (model.py:466-471, net.py:519-522) for one sigma shared by the
+ * batch: cond_out_dev[d_model].  */
+int esmdiff_time_embed(esmdiff_ctx* ctx, float sigma, float* cond_out_dev, void* stream);
+
+/* Replaces self.net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=aux,
+ * labels=None).structure_logits (model.py:475-481; net.py:371-483).
+ *   seq_dev, xt_dev : int64 [B*T]
+ *   aux_dev         : fp32, row m at aux_dev + m*aux_row_stride (stride 0 = one vector for all
+ *                     rows); NULL = no auxiliary embedding
+ *   logits_out_dev  : fp32 [B*T, n_structure_heads], row-major contiguous
+ *   embeddings_out_dev : fp32 [B*T, d_model] pre-final-norm residual stream, or NULL */
+int esmdiff_forward(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t* xt_dev, int B, int T,
+                    const float* aux_dev, int64_t aux_row_stride, float* logits_out_dev,
+                    float* embeddings_out_dev, void* stream);
+/* Same with the time embedding computed inside from sigma (_model_wrapper, model.py:464-481). */
+int esmdiff_forward_sigma(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t* xt_dev, int B,
+                          int T, float sigma, float* logits_out_dev, void* stream);
+
+/* Replaces logits_parameterization (model.py:527-533): logp_out_dev[B*T, V] (may alias logits). */
+int esmdiff_logits_parameterization(esmdiff_ctx* ctx, const float* logits_dev,
+                                    const int64_t* xt_dev, int B, int T, float* logp_out_dev,
+                                    void* stream);
+/* Replaces logits_parameterization + the tail of _ddpm_update + _sample_categorical
+ * (model.py:527-533, 602-607, 24-28).  x_inout_dev int64 [B*T] is updated in place.
+ * u_dev: the uniforms torch.rand_like(q_xs) would draw, fp32 [B*T, V]; NULL = library Philox
+ * stream keyed by (seed, step).  mc_t/mc_s: move chances 1-exp(-sigma) (model.py:592-593). */
+int esmdiff_sample_step(esmdiff_ctx* ctx, int64_t* x_inout_dev, const float* logits_dev,
+                        const float* u_dev, float mc_t, float mc_s, int B, int T, uint64_t seed,
+                        uint32_t step, void* stream);
+/* Replaces the noise-removal argmax (model.py:575-579). */
+int esmdiff_denoise_argmax(esmdiff_ctx* ctx, int64_t* x_inout_dev, const float* logits_dev, int B,
+                           int T, void* stream);
+
+/* LogLinearNoise schedule of ddpm_sample/_ddpm_update (model.py:564-567, 584-593;
+ * noise_utils.py:205-206) in C float arithmetic: sigma[steps+1], mc_t[steps], mc_s[steps]. */
+int esmdiff_schedule(int steps, float eps, float noise_eps, float* sigma, float* mc_t, float* mc_s);
+
+/* Replaces MaskedDiffusionLanguageModeling.ddpm_sample (model.py:543-581), device resident.
+ *   prior_dev : int64 [B*T] or NULL (all MASK);  out_dev : int64 [B*T]
+ *   sigma[steps+1], mc_t[steps], mc_s[steps] : host arrays (esmdiff_schedule or the caller's)
+ *   uniforms come from the library Philox stream (seed); noise_removal as model.py:575. */
+int esmdiff_ddpm_sample(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t* prior_dev, int B,
+                        int T, int steps, const float* sigma, const float* mc_t, const float* mc_s,
+                        uint64_t seed, int noise_removal, int64_t* out_dev, void* stream);
+/* Same through HOST buffers (pageable or pinned): H2D of seq/prior, the loop, D2H of the ids,
+ * stream synchronised on return.  This is the end-to-end call bench.py times as `e2e`. */
+int esmdiff_ddpm_sample_host(esmdiff_ctx* ctx, const int64_t* seq_host, const int64_t* prior_host,
+                             int B, int T, int steps, float eps, uint64_t seed, int noise_removal,
+                             int64_t* out_host);
+
+/* Waits for the stream and reports asynchronous failures: CUDA errors, out-of-range token ids
+ * (the reference raises IndexError in nn.Embedding), pipeline watchdog trips. */
+int esmdiff_synchronize(esmdiff_ctx* ctx, void* stream);
+/* Number of kernels this library has launched since create (bench.py's gpu_launches claim). */
+int64_t esmdiff_launch_count(const esmdiff_ctx* ctx);
+/* Device-event timing of the last ddpm_sample call: total ms, and ms spent in GEMM kernels is
+ * not separable here -- see bench.py which times kernels through the op entry points below. */
+
+/* ---- single-kernel entry points (unit parity tests, roofline timing) ---------------------- */
+/* C = A[M,K] (bf16) * W[N,K]^T (bf16), epilogue: 0 store bf16, 1 resid fp32 (out += acc/scale),
+ * 2 SwiGLU bf16 (W rows pre-interleaved, out [M, N/2]), 3 bias+GELU fp32, 4 bias fp32. */
+int esmdiff_op_gemm(esmdiff_ctx* ctx, int epilogue, const void* a_bf16_dev, const void* w_bf16_dev,
+                    int M, int N, int K, void* out_dev, int64_t ldo, const float* bias_dev,
+                    float scale, void* stream);
+/* y bf16 [M,D] = LayerNorm(x fp32 [M,D]) * w + b (b may be NULL), eps 1e-5. */
+int esmdiff_op_layernorm(esmdiff_ctx* ctx, const float* x_dev, const float* w_dev,
+                         const float* b_dev, void* y_bf16_dev, int M, int D, void* stream);
+/* in place on qkv bf16 [B*T, 3D]: q_ln/k_ln over D then rotary per 64-wide head. */
+int esmdiff_op_qk_norm_rope(esmdiff_ctx* ctx, void* qkv_bf16_dev, const float* q_w_dev,
+                            const float* k_w_dev, int B, int T, int D, void* stream);
+/* ctx bf16 [B*T, D] = softmax(q k^T / 8) v per head, from qkv bf16 [B*T, 3D]. */
+int esmdiff_op_attention(esmdiff_ctx* ctx, const void* qkv_bf16_dev, void* ctx_bf16_dev, int B,
+                         int T, int H, void* stream);
+/* fp32 [rows, cols] -> bf16, optional SwiGLU row interleave (swiglu_hidden > 0). */
+int esmdiff_op_convert_bf16(esmdiff_ctx* ctx, const float* src_dev, void* dst_bf16_dev,
+                            int64_t rows, int64_t cols, int swiglu_hidden, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESMDIFF_B200_H */
