@@ -206,15 +206,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,
                                         __float2bfloat16_rn(stg[r * STG_LD + lane]);
                             }
                         } else if constexpr (EPI == EPI_RESID_F32) {
-                            float* out = reinterpret_cast<float*>(p.out);
-#pragma unroll 8
-                            for (int r = 0; r < 32; ++r) {
-                                const int row = row_base + r;
-                                if (row < p.M) {
-                                    float* q = out + static_cast<long long>(row) * p.ldo + col;
-                                    *q = *q + stg[r * STG_LD + lane] / p.scale;
-                                }
-                            }
+                            // read-modify-write of the fp32 residual stream: issue all 32 loads
+                            // before the first store so they overlap (same pointer -> the
+                            // compiler would otherwise serialise load/store pairs).
+                            float* out = reinterpret_cast<float*>(p.out) +
+                                         static_cast<long long>(row_base) * p.ldo + col;
+                            float old[32];
+#pragma unroll
+                            for (int r = 0; r < 32; ++r)
+                                old[r] = (row_base + r < p.M) ? __ldcg(out + static_cast<long long>(r) * p.ldo) : 0.f;
+#pragma unroll
+                            for (int r = 0; r < 32; ++r)
+                                if (row_base + r < p.M)
+                                    out[static_cast<long long>(r) * p.ldo] =
+                                        old[r] + stg[r * STG_LD + lane] / p.scale;
                         } else {
                             float* out = reinterpret_cast<float*>(p.out);
 #pragma unroll 8

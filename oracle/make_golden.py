@@ -17,7 +17,7 @@ sampler_seeded.npz    larger sampler steps; logits/u are regenerated from stored
 schedule.npz          time grid, sigma, move chances for num_steps in {10, 25, 50}
 timestep_embedder.npz TimestepEmbedder outputs for seeded weights
 trajectory_tiny.npz   a full 25-step ddpm_sample of the reference sampler driving the tiny
-                      oracle net (d=128, 2 layers): x_t per step, final ids
+                      oracle net (d=256, 4 heads, 2 layers): x_t per step, final ids
 tokenizer_pins.json   sequence <-> token ids, BOS/EOS ids, structure-code range (from *.pth)
 chunks.json           chunk lists of sample_esmdiff.py:181-194 for the BASELINE configs
 """
@@ -148,9 +148,9 @@ def main():
              **{f"{k}_{i}": np.asarray(v) for i, c in enumerate(cases) for k, v in c.items()})
 
     # ---- full trajectory on the tiny oracle net ---------------------------------------------
-    dims = esm3_ref.Esm3Dims(d_model=128, n_heads=2, v_heads=8, n_layers=2)
+    dims = esm3_ref.Esm3Dims(d_model=256, n_heads=4, v_heads=8, n_layers=2)
     net, emb = esm3_ref.build_reference_model(dims, seed=0)
-    te_small = TE(128).eval()
+    te_small = TE(256).eval()
     te_small.load_state_dict(emb.state_dict())
     ref_small = ref_loader.build_reference_sampler(net, te_small)
     g = torch.Generator().manual_seed(0)
