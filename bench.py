@@ -1,0 +1,349 @@
+"""Benchmark of the ESMDiff ddpm sampling path (BASELINE.json metric: structure-tokens/s).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+One "step" = one complete sampling job of the workload: BASELINE config 2 -- a synthetic L=256
+protein, random-init ESM3-open-sized weights, num_steps=25 (+1 noise-removal forward),
+num_samples=100 in the reference's chunk list [63, 37] (sample_esmdiff.py:181-194).  The timed
+window is the reference's own (sample_esmdiff.py:177 -> :223, "Sampling token time").
+structure-tokens/s = num_samples * L / window time.
+
+N > 1 (torchrun, one rank per GPU): conformation samples are independent, so every rank runs the
+same 100-sample job on its own GPU (weak scaling: per-GPU work fixed; value = N*100*256 tokens /
+max-over-ranks time); weights are generated on rank 0 and broadcast once over NCCL before the
+timed region, the final tokens are all-gathered inside it.  No per-step collective exists on
+this path.
+
+`value`   : device-resident inputs, CUDA events on the launching stream, max over ranks.
+`e2e`     : the same job through the public host API (esmdiff_b200.sampling.sample_structure_tokens
+            -> MaskedDiffusionLanguageModeling.ddpm_sample) from pinned HOST token buffers to
+            HOST int64 tokens, copies inside the timed region.
+`roofline`: the dominant kernel family (tcgen05 GEMM, all epilogues) -- algorithmic FLOPs of its
+            launches / their CUDA-event durations measured live in the timed region through
+            esmdiff_profile_*; peak from MEASURED_PEAKS.json (sustained bf16) else the fallback.
+`cpu_baseline` / `--impl reference`: the CPU restatement of the reference path (oracle/: the
+            reference's sampler ops + an fp32 PyTorch ESM3 restatement; the esm package itself is
+            not installable offline) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+L_RES, N_SAMPLES, N_STEPS, EPS = 256, 100, 25, 1e-5
+T_TOK = L_RES + 2
+FALLBACK_PEAK_TFLOPS = 1400.0       # B200_PROFILING.md: sustained cuBLAS bf16 under the 1 kW cap
+FALLBACK_PEAK_GBS = 6650.0
+
+
+def forward_flops(B: int, T: int) -> float:
+    """GEMMs + attention matmuls of one forward (ESM3-open dims)."""
+    return float(B) * T * (48 * (56_623_104 + 6144 * T) + 17_316_864)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), float(d["hbm_gbs"]), "measured"
+    return FALLBACK_PEAK_TFLOPS, FALLBACK_PEAK_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.thread.join(timeout=5)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference path on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int, budget_s: float, emit_line: bool):
+    from esmdiff_b200.engine import Dims
+    from esmdiff_b200.synthetic import random_state_dict
+    from esmdiff_b200.tokenization import synthetic_sequence_tokens
+    from oracle import esm3_ref, mdlm_ref
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = random_state_dict(Dims(), device="cpu", seed=0, full=True)
+    net, emb = esm3_ref.build_from_state_dict(esm3_ref.Esm3Dims(), sd)
+    del sd
+    seq = synthetic_sequence_tokens(L_RES, seed=0)[None]          # one sample, full length T=258
+    sampler = mdlm_ref.SamplerRef(net, emb)
+    ts, dt = mdlm_ref.time_grid(N_STEPS, EPS)
+    torch.manual_seed(123)
+    x = torch.full((1, T_TOK), 4096, dtype=torch.int64)
+
+    def one_update(i, x):
+        sigma, mc_t, mc_s = mdlm_ref.move_chances(ts[i] * torch.ones(1, 1), dt)
+        logp, _ = sampler.log_p_x0(x, seq, sigma)
+        return mdlm_ref.ddpm_update_tail(logp, x, mc_t, mc_s, torch.rand_like(logp))
+
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        x = one_update(0, x)                                       # calibration (also warms the allocator)
+    t_fwd = time.perf_counter() - t0
+    n_iter = max(1, steps + warmup)
+    f = int(max(1, min(N_STEPS + 1, budget_s / max(t_fwd, 1e-3) / n_iter)))
+    times = []
+    with torch.no_grad():
+        for it in range(n_iter):
+            t0 = time.perf_counter()
+            for j in range(f):
+                x = one_update(min(j, N_STEPS - 1), x)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    per_update = sum(times) / (len(times) * f)
+    job_s = per_update * (N_STEPS + 1)                              # 25 updates + 1 noise-removal forward
+    value = L_RES / job_s                                           # 1 sample of L tokens per job
+    sample = (f"1 of {N_SAMPLES} samples (B=1, T={T_TOK}), {f} of {N_STEPS + 1} forward+update passes per "
+              f"step, fp32 torch CPU; tokens/s = {L_RES} / ({N_STEPS + 1} x mean pass time)")
+    base = {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+    if not emit_line:
+        return base
+    ms = sum(times) / len(times) * 1e3
+    line = {"impl": "reference", "metric": "structure_tokens_per_sec", "value": value, "unit": "tokens/s",
+            "n_gpus": 0, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(), "cpu_baseline": base,
+            "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return base
+
+
+def workload_config(chunks=None, n_gpus=1, rng="philox"):
+    from esmdiff_b200.sampling import chunk_sizes
+    chunks = chunks or chunk_sizes(T_TOK, N_SAMPLES)
+    return {"workload": "config2: synthetic L=256 protein, random-init ESM3-open dims (d=1536, 48 layers, "
+                        "24 heads, V=4101), num_steps=25 + noise removal, num_samples=100 per GPU",
+            "L": L_RES, "T": T_TOK, "num_samples_per_gpu": N_SAMPLES, "num_steps": N_STEPS,
+            "chunks": chunks, "uniforms": rng, "parallelism": f"independent samples x{n_gpus}",
+            "l2": "inputs larger than L2 (2.7 GB of bf16 weights streamed per forward)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def gpu_bench(args):
+    from esmdiff_b200 import distributed as D
+    from esmdiff_b200.engine import Dims, Engine
+    from esmdiff_b200.model import MaskedDiffusionLanguageModeling
+    from esmdiff_b200.noise_utils import LogLinearNoise
+    from esmdiff_b200.sampling import chunk_sizes, sample_structure_tokens
+    from esmdiff_b200.synthetic import random_state_dict
+    from esmdiff_b200.tokenization import synthetic_sequence_tokens
+
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dims = Dims()
+    eng = Engine(dims, device=local)
+    sd = random_state_dict(dims, device=dev, seed=0) if rank == 0 else None
+    sd = D.broadcast_state_dict(sd, dev)                            # the one NCCL weight broadcast
+    eng.load_state_dict(sd)
+    del sd
+    torch.cuda.empty_cache()
+
+    class Net:                                                      # CustomizedESM3 surface over the engine
+        engine, device, output_heads = eng, dev, None
+
+    model = MaskedDiffusionLanguageModeling(net=Net(), noise_schedule=LogLinearNoise(), sigma_embedder=None,
+                                            time_conditioning=True, noise_removal=True, rng=args.rng)
+    chunks = [N_SAMPLES] if args.chunks == "full" else chunk_sizes(T_TOK, N_SAMPLES)
+    seq_host = synthetic_sequence_tokens(L_RES, seed=0).pin_memory()
+    seq_dev = seq_host.to(dev)
+    sigma, mc_t, mc_s = model._schedule(N_STEPS, EPS, 1.0, dev)
+    counts = [N_SAMPLES] * world
+
+    def job_resident(step_idx):
+        outs = []
+        for ci, bs in enumerate(chunks):
+            batch = seq_dev[None].expand(bs, T_TOK).contiguous()
+            outs.append(eng.ddpm_sample(batch, None, N_STEPS, sigma, mc_t, mc_s,
+                                        seed=1000 * step_idx + 17 * rank + ci))
+        tok = torch.cat(outs)[:, 1:-1].contiguous()
+        return D.gather_tokens(tok, counts)
+
+    def job_e2e(step_idx):
+        torch.manual_seed(123 + step_idx + 1000 * rank)
+        tok, _ = sample_structure_tokens(model, seq_host, N_SAMPLES, N_STEPS, eps=EPS, chunks=chunks,
+                                         verbose=False)
+        tok = D.gather_tokens(tok, counts)
+        return tok.to("cpu", non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for w in range(args.warmup):
+        job_resident(-1 - w)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    eng.profile(True)
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        tok = job_resident(k)
+    e1.record()
+    barrier()
+    eng.synchronize()
+    launches = eng.launch_count - l0
+    eng.profile(False)
+    ms_total = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    clk = clocks.stop() if rank == 0 else None
+    prof = eng.profile_read()
+    assert tok.shape == (N_SAMPLES * world, L_RES) and int((tok == 4096).sum()) == 0
+
+    # ---- end to end through the host API ------------------------------------------------------
+    for w in range(min(args.warmup, 1)):
+        job_e2e(-1 - w)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        tok_host = job_e2e(k)
+    torch.cuda.synchronize(dev)
+    e2e_s = D.max_over_ranks(time.perf_counter() - t0, dev)
+    if world > 1:
+        torch.distributed.barrier()
+    assert not tok_host.is_cuda and tok_host.shape == (N_SAMPLES * world, L_RES)
+
+    tokens_per_step = N_SAMPLES * L_RES * world
+    ms_per_step = ms_total / args.steps
+    value = tokens_per_step / (ms_per_step * 1e-3)
+    e2e_value = tokens_per_step / (e2e_s / args.steps)
+
+    peak_tf, peak_gbs, how = measured_peaks()
+    gemm = [prof[k] for k in ("gemm_store_bf16", "gemm_resid_f32", "gemm_swiglu", "gemm_bias_gelu", "gemm_bias")]
+    g_ms, g_fl, g_n = (sum(x[i] for x in gemm) for i in range(3))
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    fwd_flops = (N_STEPS + 1) * sum(forward_flops(b, T_TOK) for b in chunks)
+    kernels = {}
+    for name, (ms, work, n) in prof.items():
+        if n == 0:
+            continue
+        tensor = name.startswith("gemm") or name == "attention"
+        kernels[name] = {"launches": n, "ms_total": round(ms, 3), "share_of_step": round(ms / ms_total, 4),
+                         ("tflops" if tensor else "gbs"): round(work / (ms * 1e-3) / (1e12 if tensor else 1e9), 1)}
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (tcgen05, all epilogues)",
+                "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(achieved / peak_tf, 4), "peak_source": f"{how} bf16 sustained",
+                "launches": g_n, "avg_launch_ms": round(g_ms / max(g_n, 1), 4),
+                "flops_per_launch": g_fl / max(g_n, 1), "share_of_step": round(g_ms / ms_total, 4),
+                "traffic": None,
+                "whole_job": {"algorithmic_tflop_per_step": round(fwd_flops / 1e12, 1),
+                              "tflops": round(fwd_flops / (ms_per_step * 1e-3) / 1e12, 1),
+                              "frac": round(fwd_flops / (ms_per_step * 1e-3) / 1e12 / peak_tf, 4)},
+                "kernels": kernels}
+
+    if rank == 0:
+        line = {"metric": "structure_tokens_per_sec", "value": round(value, 1), "unit": "tokens/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms_per_step, 2), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(chunks, world, args.rng), "clocks": clk,
+                "e2e": {"value": round(e2e_value, 1), "unit": "tokens/s",
+                        "h2d_bytes_per_step": int(N_SAMPLES * T_TOK * 8),
+                        "d2h_bytes_per_step": int(tok_host.numel() * 8),
+                        "api": "esmdiff_b200.sampling.sample_structure_tokens (pinned host tokens in, host "
+                               "int64 tokens out), uniforms=" + args.rng},
+                "gpu_launches": int(launches), "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(1, 0, 20.0, emit_line=False)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunks", default="reference", choices=["reference", "full"],
+                    help="reference: sample_esmdiff.py chunk list [63, 37]; full: one batch of 100")
+    ap.add_argument("--rng", default="philox", choices=["philox", "torch"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return                                                   # rank 0 alone runs the CPU arm
+        cpu_reference(args.steps, args.warmup, 150.0, emit_line=True)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun when called as plain `python bench.py --gpus N`
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    gpu_bench(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,9 @@ _SIGS = {
                                            C.c_uint64, C.c_int, _P]),
     "esmdiff_synchronize": (C.c_int, [_P, _P]),
     "esmdiff_launch_count": (C.c_int64, [_P]),
+    "esmdiff_profile_enable": (C.c_int, [_P, C.c_int]),
+    "esmdiff_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_int64)]),
     "esmdiff_op_gemm": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64,
                                   _P, C.c_float, _P]),
     "esmdiff_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),

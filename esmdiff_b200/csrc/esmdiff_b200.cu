@@ -75,6 +75,21 @@ struct esmdiff_ctx {
 
     std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> tmaps;
 
+    // optional per-launch device timing (esmdiff_profile_*): CUDA events on the launching stream
+    struct ProfRec { int kind; double work; cudaEvent_t a, b; };
+    bool prof = false;
+    std::vector<ProfRec> prof_recs;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t next_event() {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev_pool.push_back(e);
+        }
+        return ev_pool[ev_used++];
+    }
+
     int fail(const std::string& m) {
         err = m;
         return 1;
@@ -87,6 +102,26 @@ struct esmdiff_ctx {
         owned.push_back(q);
         *p = reinterpret_cast<T*>(q);
         return 0;
+    }
+};
+
+// Records an event pair around one kernel launch while profiling is on.
+struct ProfScope {
+    esmdiff_ctx* c;
+    cudaStream_t st;
+    size_t idx = 0;
+    bool on;
+    ProfScope(esmdiff_ctx* c_, int kind, double work, cudaStream_t st_) : c(c_), st(st_), on(c_->prof) {
+        if (!on) return;
+        esmdiff_ctx::ProfRec r;
+        r.kind = kind; r.work = work;
+        r.a = c->next_event(); r.b = c->next_event();
+        cudaEventRecord(r.a, st);
+        idx = c->prof_recs.size();
+        c->prof_recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(c->prof_recs[idx].b, st);
     }
 };
 
@@ -140,6 +175,7 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+    ProfScope prof(c, epi, 2.0 * M * (double)N * K, st);
 #define LAUNCH_GEMM(E)                                                                         \
     case E: {                                                                                  \
         static bool attr_set = false;                                                          \
@@ -169,6 +205,7 @@ static int launch_layernorm(esmdiff_ctx* c, const float* x, const float* w, cons
                             int M, int D, cudaStream_t st) {
     if (D % 128 != 0 || D > 128 * 12) return c->fail("layernorm: D must be a multiple of 128, <= 1536");
     const int grid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    ProfScope prof(c, ESMDIFF_PROF_LAYERNORM, 6.0 * M * D, st);
     ew::layernorm_f32_to_bf16_kernel<12><<<grid, ew::ROWS_PER_BLOCK * 32, 0, st>>>(x, w, b, y, M, D, 1e-5f);
     c->launches++;
     CK(cudaGetLastError());
@@ -199,6 +236,7 @@ static int launch_qk_norm_rope(esmdiff_ctx* c, bf16* qkv, const float* qw, const
     if (D % 256 != 0 || D > 256 * 6) return c->fail("qk_norm_rope: D must be a multiple of 256, <= 1536");
     if (ensure_rope(c, T, st)) return 1;
     const int grid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    ProfScope prof(c, ESMDIFF_PROF_QK_NORM_ROPE, 8.0 * M * D, st);
     ew::qk_layernorm_rope_kernel<6><<<grid, ew::ROWS_PER_BLOCK * 32, 0, st>>>(qkv, qw, kw, c->cos_t,
                                                                                c->sin_t, M, D, T, 1e-5f);
     c->launches++;
@@ -224,6 +262,7 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
         attr_set = true;
     }
     const int grid = B * H * p.q_tiles;
+    ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn::DH, st);
     attn::attention_fwd_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tq, tkv, p);
     c->launches++;
     CK(cudaGetLastError());
@@ -282,10 +321,13 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
     const float rs = sqrtf((float)c->cfg.n_layers / 36.0f);
 
     const int rgrid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    {
+    ProfScope prof(c, ESMDIFF_PROF_EMBED, 12.0 * M * D, st);
     ew::embed_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const long long*>(seq),
                                             reinterpret_cast<const long long*>(xt), c->seq_embed,
                                             c->struct_embed, c->const_vec, aux, aux_stride, c->x, M, D,
                                             c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err);
+    }
     c->launches++;
     CK(cudaGetLastError());
 
@@ -314,6 +356,7 @@ static int launch_sampler(esmdiff_ctx* c, const float* logits, const float* u, i
                           int M, float mc_t, float mc_s, uint64_t seed, uint32_t step, cudaStream_t st) {
     const int V = c->cfg.n_structure_heads;
     if (V > sampler::THREADS * sampler::MAX_PER_THREAD) return c->fail("sampler: vocabulary too large");
+    ProfScope prof(c, ESMDIFF_PROF_SAMPLER, (u ? 8.0 : 4.0) * M * V, st);
     sampler::sample_rows_kernel<MODE><<<M, sampler::THREADS, 0, st>>>(
         logits, (long long)V, u, reinterpret_cast<long long*>(x), logp, M, V,
         ESMDIFF_STRUCTURE_MASK_TOKEN, mc_t, mc_s, (unsigned long long)seed, step);
@@ -326,6 +369,10 @@ static int launch_sampler(esmdiff_ctx* c, const float* logits, const float* u, i
 // weights
 // ------------------------------------------------------------------------------------------------
 namespace {
+__global__ void fill_i64_kernel(long long* p, long long v, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 __global__ void bf16_to_f32_kernel(const bf16* s, float* d, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __bfloat162float(s[i]);
@@ -487,6 +534,7 @@ int esmdiff_destroy(esmdiff_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->owned)
         if (p) cudaFree(p);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     delete c;
     return 0;
 }
@@ -646,9 +694,10 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
     if (prior) {
         CK(cudaMemcpyAsync(out, prior, (size_t)M * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     } else {
-        std::vector<int64_t> h((size_t)M, (int64_t)ESMDIFF_STRUCTURE_MASK_TOKEN);
-        CK(cudaMemcpyAsync(out, h.data(), (size_t)M * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));
+        fill_i64_kernel<<<(M + 255) / 256, 256, 0, st>>>(reinterpret_cast<long long*>(out),
+                                                         ESMDIFF_STRUCTURE_MASK_TOKEN, M);
+        c->launches++;
+        CK(cudaGetLastError());
     }
     for (int i = 0; i < steps; ++i) {
         if (launch_time_embed(c, sigma[i], c->cond, st)) return 1;
@@ -711,6 +760,30 @@ int esmdiff_ddpm_sample_host(esmdiff_ctx* c, const int64_t* seq_host, const int6
 }
 
 int64_t esmdiff_launch_count(const esmdiff_ctx* c) { return c ? c->launches : 0; }
+
+int esmdiff_profile_enable(esmdiff_ctx* c, int on) {
+    if (!c) return 1;
+    if (on) {
+        c->prof_recs.clear();
+        c->ev_used = 0;
+    }
+    c->prof = on != 0;
+    return 0;
+}
+
+int esmdiff_profile_read(esmdiff_ctx* c, int kind, double* ms, double* work, int64_t* launches) {
+    if (!c || !ms || !work || !launches) return 1;
+    CK(cudaSetDevice(c->device));
+    *ms = 0.0; *work = 0.0; *launches = 0;
+    for (const auto& r : c->prof_recs) {
+        if (r.kind != kind) continue;
+        CK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, r.a, r.b));
+        *ms += t; *work += r.work; *launches += 1;
+    }
+    return 0;
+}
 
 int esmdiff_op_gemm(esmdiff_ctx* c, int epi, const void* a, const void* w, int M, int N, int K, void* out,
                     int64_t ldo, const float* bias, float scale, void* stream) {

@@ -80,3 +80,22 @@ def gather_tokens(local_tokens: torch.Tensor, counts: list[int]) -> torch.Tensor
     bufs = [torch.empty_like(pad) for _ in counts]
     dist.all_gather(bufs, pad)
     return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """MAX all-reduce of one float (device-timed milliseconds in bench.py)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64,
+                     device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())

@@ -87,6 +87,22 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.L.esmdiff_launch_count(self.h))
 
+    PROF_KINDS = {"gemm_store_bf16": 0, "gemm_resid_f32": 1, "gemm_swiglu": 2, "gemm_bias_gelu": 3,
+                  "gemm_bias": 4, "attention": 5, "sampler": 6, "layernorm": 7, "qk_norm_rope": 8,
+                  "embed": 9}
+
+    def profile(self, on: bool):
+        self._check(self.L.esmdiff_profile_enable(self.h, int(on)))
+
+    def profile_read(self) -> dict:
+        """{kind: (ms, work, launches)} measured with CUDA events around each launch."""
+        out = {}
+        for name, k in self.PROF_KINDS.items():
+            ms, work, n = C.c_double(), C.c_double(), C.c_int64()
+            self._check(self.L.esmdiff_profile_read(self.h, k, C.byref(ms), C.byref(work), C.byref(n)))
+            out[name] = (ms.value, work.value, n.value)
+        return out
+
     # -- weights ----------------------------------------------------------------------------
     def set_weight(self, key: str, tensor: torch.Tensor):
         t = tensor.detach()

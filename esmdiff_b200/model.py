@@ -12,7 +12,8 @@ Differences that do not change results:
 Uniforms: ``rng="torch"`` draws ``torch.rand(B, T, 4101)`` per step from torch's CUDA generator --
 the same call, shape and order as the reference's ``torch.rand_like(q_xs)`` (model.py:25-27), so
 with ``torch.manual_seed(s)`` both consume the same stream.  ``rng="philox"`` uses the library's
-counter-based generator inside the sampling kernel (no 4101-wide uniform tensor in HBM).
+counter-based generator inside the sampling kernel (no 4101-wide uniform tensor in HBM); its key
+is drawn once per ``ddpm_sample`` call from torch's CPU generator.
 """
 from __future__ import annotations
 
@@ -160,7 +161,10 @@ class MaskedDiffusionLanguageModeling(nn.Module):
         sigma, mc_t, mc_s = self._schedule(num_steps, eps, sample_max_t, self.device)
         eng = self.engine
         if self.rng == "philox":
-            seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF) if seed is None else seed
+            if seed is None:
+                # one draw from torch's CPU generator per call: reproducible under
+                # torch.manual_seed and different for every chunk of a run
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             return eng.ddpm_sample(seq, x, num_steps, sigma, mc_t, mc_s, seed=seed,
                                    noise_removal=self.noise_removal)
         B, T = x.shape

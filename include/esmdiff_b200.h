@@ -114,8 +114,25 @@ int esmdiff_ddpm_sample_host(esmdiff_ctx* ctx, const int64_t* seq_host, const in
 int esmdiff_synchronize(esmdiff_ctx* ctx, void* stream);
 /* Number of kernels this library has launched since create (bench.py's gpu_launches claim). */
 int64_t esmdiff_launch_count(const esmdiff_ctx* ctx);
-/* Device-event timing of the last ddpm_sample call: total ms, and ms spent in GEMM kernels is
- * not separable here -- see bench.py which times kernels through the op entry points below. */
+
+/* Per-kernel device timing for roofline reports (bench.py): while enabled, every launch of the
+ * kinds below is bracketed by CUDA events on its own stream.  esmdiff_profile_read sums, for one
+ * kind, the event-measured milliseconds, the algorithmic work (FLOPs for the tensor-core kernels,
+ * bytes for the HBM-bound ones) and the launch count since the last enable(1). */
+enum esmdiff_prof_kind {
+    ESMDIFF_PROF_GEMM_STORE_BF16 = 0, /* QKV projection                         FLOPs */
+    ESMDIFF_PROF_GEMM_RESID_F32 = 1,  /* out_proj / FFN W2 + residual           FLOPs */
+    ESMDIFF_PROF_GEMM_SWIGLU = 2,     /* FFN W1 + SwiGLU                        FLOPs */
+    ESMDIFF_PROF_GEMM_BIAS_GELU = 3,  /* head Linear + GELU                     FLOPs */
+    ESMDIFF_PROF_GEMM_BIAS = 4,       /* head output Linear                     FLOPs */
+    ESMDIFF_PROF_ATTENTION = 5,       /*                                        FLOPs */
+    ESMDIFF_PROF_SAMPLER = 6,         /* logits (+ uniforms) read               bytes */
+    ESMDIFF_PROF_LAYERNORM = 7,       /* fp32 in + bf16 out                     bytes */
+    ESMDIFF_PROF_QK_NORM_ROPE = 8,    /* q,k bf16 in + out                      bytes */
+    ESMDIFF_PROF_EMBED = 9            /* two gathers + one store, fp32          bytes */
+};
+int esmdiff_profile_enable(esmdiff_ctx* ctx, int on);
+int esmdiff_profile_read(esmdiff_ctx* ctx, int kind, double* ms, double* work, int64_t* launches);
 
 /* ---- single-kernel entry points (unit parity tests, roofline timing) ---------------------- */
 /* C = A[M,K] (bf16) * W[N,K]^T (bf16), epilogue: 0 store bf16, 1 resid fp32 (out += acc/scale),

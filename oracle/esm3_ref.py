@@ -297,6 +297,19 @@ def build_reference_model(dims: Esm3Dims | None = None, seed: int = 0):
     return net, emb
 
 
+def build_from_state_dict(dims: Esm3Dims, sd: dict):
+    """Oracle modules holding the tensors of a DeepSpeed-style ``['module']`` dict (keys ``net.*``
+    and ``sigma_embedder.*``) without running the default initialisers (meta device + assign)."""
+    with torch.device("meta"):
+        net = CustomizedESM3Ref(dims)
+        emb = TimestepEmbedderRef(dims.d_model)
+    net.load_state_dict({k[4:]: v.detach().float().cpu() for k, v in sd.items() if k.startswith("net.")},
+                        strict=True, assign=True)
+    emb.load_state_dict({k[15:]: v.detach().float().cpu() for k, v in sd.items()
+                         if k.startswith("sigma_embedder.")}, strict=True, assign=True)
+    return net.eval(), emb.eval()
+
+
 def full_state_dict(net: nn.Module, emb: nn.Module) -> dict:
     """Keys as in a DeepSpeed ``['module']`` dict (checkpoint_utils.py:62-64)."""
     sd = {f"net.{k}": v for k, v in net.state_dict().items()}

@@ -1,0 +1,267 @@
+"""GPU: the whole ddpm path through the reference-shaped host API, against the oracle.
+
+Parity tiers:
+  T1  fused sampling kernel == reference `_ddpm_update` tail given identical (logits, u, x):
+      token ids bit-exact (documented near-tie exemption, counted).
+  T2  forward vs the fp32 CPU oracle, teacher-forced on the oracle's x_t at every step.
+      Tolerance (written here, measured on B200): bf16 GEMM operands + fp32 accumulate/residual
+      give rel-Frobenius <= 1e-2 on raw logits for the 2-layer tiny model and <= 3e-2 for the
+      48-layer ESM3-open-sized model; masked-row log-probs (post logits_parameterization) within
+      the same relative bound of their spread.
+  T3  free-running agreement with the oracle trajectory: reported, not asserted to be 100 %
+      (bf16 vs fp32 argmax near-ties diverge; even reference-GPU vs reference-CPU would).
+  T4  a reference-style sampler (torch ops, the oracle's restatement of model.py:543-607 --
+      pinned bit-for-bit to the reference in the build container) driving the CUDA-backed
+      ``CustomizedESM3`` reproduces the fused kernels step by step.
+Full-size checks (BASELINE config 2 / 4 shapes) use size-independent properties.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import esm3_ref, mdlm_ref
+
+pytestmark = pytest.mark.gpu
+MASK = 4096
+DEV = "cuda"
+
+
+def rel_fro(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
+def make_seq(B, T, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    row = torch.cat([torch.zeros(1, dtype=torch.long), torch.randint(4, 24, (T - 2,), generator=g),
+                     torch.full((1,), 2)])
+    return row[None].repeat(B, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# tiny model: golden trajectory, teacher-forced
+# ---------------------------------------------------------------------------------------------
+def test_teacher_forced_trajectory_tiny(tiny_pair, golden_dir):
+    net, emb, eng = tiny_pair
+    g = np.load(golden_dir / "trajectory_tiny.npz")
+    seq = torch.from_numpy(g["seq"])
+    rec = []
+    torch.manual_seed(int(g["sample_seed"]))
+    x_final = mdlm_ref.SamplerRef(net, emb, record=rec).ddpm_sample(seq, 25)
+    assert np.array_equal(x_final.numpy(), g["x_final"])            # oracle == reference-made fixture
+    assert np.array_equal(np.stack([r["x_t"].numpy() for r in rec]), g["x_t"])
+    B = seq.shape[0]
+    excused = 0
+    worst = 0.0
+    agree = []
+    for r in rec[:-1]:
+        x_t = r["x_t"]
+        logits = eng.forward_sigma(seq, x_t.to(DEV), r["sigma_t"])
+        eng.synchronize()
+        e = rel_fro(logits.cpu(), r["raw_logits"])
+        worst = max(worst, e)
+        assert e < 1e-2, f"step {r['step']}: logits rel_fro {e:.3e}"                      # T2
+        mct = torch.full((B, 1, 1), r["mc_t"])
+        mcs = torch.full((B, 1, 1), r["mc_s"])
+        # T1: the kernel on the ORACLE's logits and uniforms
+        got = eng.sample_step(x_t.clone().to(DEV), r["raw_logits"].to(DEV).contiguous(), r["u"].to(DEV),
+                              r["mc_t"], r["mc_s"])
+        eng.synchronize()
+        lp = mdlm_ref.logits_parameterization(r["raw_logits"].clone(), x_t)
+        excused += mdlm_ref.assert_ids_match(got.cpu(), r["x_next"], lp, mct, mcs, r["u"])
+        # T3 (reported): the kernel on ITS OWN logits
+        own = eng.sample_step(x_t.clone().to(DEV), logits, r["u"].to(DEV), r["mc_t"], r["mc_s"])
+        eng.synchronize()
+        m = x_t == MASK
+        agree.append(float((own.cpu()[m] == r["x_next"][m]).float().mean()) if bool(m.any()) else 1.0)
+    last = rec[-1]                                                                          # noise removal
+    got = eng.denoise_argmax(last["x_t"].clone().to(DEV), last["raw_logits"].to(DEV).contiguous())
+    eng.synchronize()
+    assert torch.equal(got.cpu(), last["x_next"])
+    print(f"\n[T2] worst logits rel_fro {worst:.2e}; [T1] near-tie rows excused {excused}; "
+          f"[T3] per-step agreement on own logits min {min(agree):.3f} mean {sum(agree) / len(agree):.3f}")
+    assert excused <= 2
+    assert sum(agree) / len(agree) > 0.9
+
+
+def test_reference_style_sampler_drives_cuda_net(tiny_pair):
+    """T4: the sampler half in plain torch ops (oracle restatement of the reference's
+    ddpm_sample) calls ``net(structure_tokens=, sequence_tokens=, auxiliary_embeddings=,
+    labels=None)`` on the CUDA-backed CustomizedESM3 mirror exactly like model.py:475-480."""
+    from esmdiff_b200.net import ESMOutput
+    net_o, emb_o, eng = tiny_pair
+
+    class Net(torch.nn.Module):          # CustomizedESM3.forward surface over the shared engine
+        def forward(self, structure_tokens, labels=None, mask=None, sequence_tokens=None, *,
+                    auxiliary_embeddings=None):
+            assert labels is None
+            logits, _ = eng.forward(sequence_tokens, structure_tokens, aux=auxiliary_embeddings)
+            return ESMOutput(sequence_logits=None, structure_logits=logits)
+
+    te = esm3_ref.TimestepEmbedderRef(256).to(DEV).eval()
+    te.load_state_dict(emb_o.state_dict())
+    seq = make_seq(3, 50, seed=4)
+    rec = []
+    torch.manual_seed(5)
+    sampler = mdlm_ref.SamplerRef(Net(), te, record=rec, device=DEV)
+    out = sampler.ddpm_sample(seq, 12)
+    assert out.shape == (3, 50) and out.is_cuda and int((out == MASK).sum()) == 0
+    excused = 0
+    for r in rec[:-1]:
+        B = r["x_t"].shape[0]
+        got = eng.sample_step(r["x_t"].clone(), r["raw_logits"].contiguous(), r["u"], r["mc_t"], r["mc_s"])
+        eng.synchronize()
+        mct = torch.full((B, 1, 1), r["mc_t"])
+        mcs = torch.full((B, 1, 1), r["mc_s"])
+        lp = mdlm_ref.logits_parameterization(r["raw_logits"].cpu().clone(), r["x_t"].cpu())
+        excused += mdlm_ref.assert_ids_match(got.cpu(), r["x_next"].cpu(), lp, mct, mcs, r["u"].cpu())
+        # aux as a full (B,T,d) tensor (what the reference passes) == one shared vector
+        l2 = eng.forward_sigma(seq, r["x_t"], r["sigma_t"])
+        eng.synchronize()
+        assert rel_fro(l2, r["raw_logits"]) < 1e-6
+    assert excused <= 2
+
+
+def test_host_mirror_model_loop_matches_stepwise(tiny_pair):
+    """MaskedDiffusionLanguageModeling.ddpm_sample (rng='torch') == driving forward_sigma +
+    sample_step by hand with the same torch CUDA generator stream; rng='philox' == the C loop."""
+    from esmdiff_b200.model import MaskedDiffusionLanguageModeling
+    from esmdiff_b200.noise_utils import LogLinearNoise
+    _, emb_o, eng = tiny_pair
+
+    class NetShim:
+        engine = eng
+        device = eng.device
+        output_heads = None
+
+    m = MaskedDiffusionLanguageModeling(net=NetShim(), noise_schedule=LogLinearNoise(), sigma_embedder=None,
+                                        time_conditioning=True, noise_removal=True)
+    seq = make_seq(2, 33, seed=7)
+    torch.manual_seed(21)
+    a = m.ddpm_sample(seq, num_steps=9)
+    sigma, mc_t, mc_s = m._schedule(9, 1e-5, 1.0, DEV)
+    torch.manual_seed(21)
+    x = torch.full((2, 33), MASK, device=DEV)
+    for i in range(9):
+        logits = eng.forward_sigma(seq, x, sigma[i])
+        u = torch.rand(2, 33, 4101, device=DEV)
+        eng.sample_step(x, logits, u, mc_t[i], mc_s[i])
+    logits = eng.forward_sigma(seq, x, sigma[9])
+    eng.denoise_argmax(x, logits)
+    eng.synchronize()
+    assert torch.equal(a, x)
+    # assertion behaviour of the reference (model.py:556,562)
+    with pytest.raises(AssertionError):
+        m.ddpm_sample(seq, num_steps=3, sample_max_t=0.5)
+    with pytest.raises(AssertionError):
+        m.ddpm_sample(seq, num_steps=3, input_prior=torch.full((2, 30), MASK))
+    m.rng = "philox"
+    b1 = m.ddpm_sample(seq, num_steps=9, seed=3)
+    b2 = eng.ddpm_sample(seq, None, 9, sigma, mc_t, mc_s, seed=3)
+    b3 = m.ddpm_sample(seq, num_steps=9, seed=4)
+    eng.synchronize()
+    assert torch.equal(b1, b2) and not torch.equal(b1, b3)
+    host = eng.ddpm_sample_host(seq.contiguous(), None, 9, seed=3)
+    # host entry point evaluates the schedule in C floats (<= 2 ulp from torch's): same ids unless
+    # a uniform lands within 1e-7 of a move-chance boundary
+    assert float((host.to(DEV) == b1).float().mean()) > 0.98
+
+
+def test_inpainting_tiny(tiny_pair):
+    from esmdiff_b200.sampling import build_prior
+    _, _, eng = tiny_pair
+    T = 60
+    seq = make_seq(4, T, seed=8)
+    g = torch.Generator().manual_seed(1)
+    st = torch.randint(0, 4096, (T,), generator=g)
+    st[0], st[-1] = 4098, 4097
+    prior = build_prior(st, 4, mask_ids=list(range(1, 33)))
+    out = eng.ddpm_sample(seq, prior, 25, *eng.schedule(25), seed=2)
+    eng.synchronize()
+    out = out.cpu()
+    known = prior != MASK
+    assert torch.equal(out[known], prior[known])                   # never resampled (model.py:606-607)
+    assert int((out == MASK).sum()) == 0
+    assert len({tuple(r.tolist()) for r in out[:, 1:33]}) > 1      # samples differ
+
+
+# ---------------------------------------------------------------------------------------------
+# ESM3-open-sized model (d=1536, 48 layers, 24 heads)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_model():
+    from esmdiff_b200.engine import Dims, Engine
+    from esmdiff_b200.synthetic import random_state_dict
+    dims = Dims()
+    sd = random_state_dict(dims, device=DEV, seed=0, full=True)
+    eng = Engine(dims)
+    eng.load_state_dict(sd)
+    yield eng, sd
+    eng.close()
+
+
+def test_full_size_forward_vs_oracle(full_model):
+    """T2 at the real architecture (config-1 shape B=4 -> here B=2, T=60 so the fp32 CPU oracle
+    finishes in seconds)."""
+    eng, sd = full_model
+    net, emb = esm3_ref.build_from_state_dict(esm3_ref.Esm3Dims(), sd)
+    B, T = 2, 60
+    seq = make_seq(B, T, seed=1)
+    g = torch.Generator().manual_seed(2)
+    xt = torch.randint(0, 4096, (B, T), generator=g)
+    xt[torch.rand(B, T, generator=g) < 0.5] = MASK
+    sigma = 0.9
+    with torch.no_grad():
+        cond = emb(torch.tensor([sigma]))[0]
+        ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond[None, None].expand(B, T, -1))
+    logits, embd = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(sigma), want_embeddings=True)
+    eng.synchronize()
+    e_emb = rel_fro(embd.cpu(), ref.embeddings)
+    e_log = rel_fro(logits.cpu(), ref.structure_logits)
+    m = xt == MASK
+    lp_ref = mdlm_ref.logits_parameterization(ref.structure_logits.clone(), xt)[m][:, :4096]
+    lp_got = mdlm_ref.logits_parameterization(logits.cpu().clone(), xt)[m][:, :4096]
+    e_lp = float((lp_got - lp_ref).abs().max())
+    spread = float(lp_ref.max() - lp_ref.min())
+    top1 = float((lp_got.argmax(-1) == lp_ref.argmax(-1)).float().mean())
+    print(f"\n[T2 full size] embeddings rel_fro {e_emb:.2e}, logits rel_fro {e_log:.2e}, "
+          f"masked-row log-prob max abs err {e_lp:.3e} (spread {spread:.2f}), argmax agreement {top1:.3f}")
+    assert e_emb < 1e-2 and e_log < 3e-2
+    assert e_lp < 3e-2 * max(spread, 1.0)
+
+
+def test_config2_full_run_properties(full_model):
+    """BASELINE config 2 in full (L=256, 100 samples, 25 steps, reference chunk list [63, 37])."""
+    from esmdiff_b200.sampling import chunk_sizes
+    eng, _ = full_model
+    T = 258
+    row = make_seq(1, T, seed=0)[0]
+    sched = eng.schedule(25)
+    outs = []
+    for ci, bs in enumerate(chunk_sizes(T, 100)):
+        outs.append(eng.ddpm_sample(row[None].repeat(bs, 1), None, 25, *sched, seed=100 + ci))
+    eng.synchronize()
+    tok = torch.cat(outs)[:, 1:-1].cpu()
+    assert tok.shape == (100, 256)
+    assert int(tok.min()) >= 0 and int(tok.max()) <= 4100 and int((tok == MASK).sum()) == 0
+    assert len({tuple(r.tolist()) for r in tok}) == 100            # i.i.d. samples, all distinct
+    again = eng.ddpm_sample(row[None].repeat(63, 1), None, 25, *sched, seed=100)
+    eng.synchronize()
+    assert torch.equal(again, outs[0])                              # deterministic in the seed
+
+
+def test_config4_inpainting_full_size(full_model):
+    """BASELINE config 4: mask_ids 1..32 on L=256 (token positions, the reference's off-by-one)."""
+    from esmdiff_b200.sampling import build_prior
+    eng, _ = full_model
+    T = 258
+    row = make_seq(1, T, seed=0)[0].clone()
+    row[2:34] = 32                                                  # residues 1..32 -> '_' (mask id)
+    g = torch.Generator().manual_seed(1)
+    st = torch.randint(0, 4096, (T,), generator=g)
+    st[0], st[-1] = 4098, 4097
+    prior = build_prior(st, 37, mask_ids=list(range(1, 33)))
+    out = eng.ddpm_sample(row[None].repeat(37, 1), prior, 25, *eng.schedule(25), seed=5).cpu()
+    eng.synchronize()
+    known = prior != MASK
+    assert int(known.sum()) == 37 * (T - 32)
+    assert torch.equal(out[known], prior[known]) and int((out == MASK).sum()) == 0

@@ -45,24 +45,7 @@ def test_sampler_full_vector(golden_dir):
     assert np.array_equal(mdlm_ref.ddpm_update_tail(lp, x, mct, mcs, u).numpy(), g["x_next"])
 
 
-def _seeded_case(seed, B, T, frac, scale):
-    g = torch.Generator().manual_seed(seed)
-    logits = torch.randn(B, T, 4101, generator=g) * scale
-    u = torch.rand(B, T, 4101, generator=g)
-    x = torch.randint(0, 4096, (B, T), generator=g)
-    x = torch.where(torch.rand(B, T, generator=g) < frac, torch.full_like(x, MASK), x)
-    return logits, u, x
-
-
-def seeded_cases(golden_dir):
-    g = np.load(golden_dir / "sampler_seeded.npz")
-    for i in range(int(g["n"])):
-        c = {k[: -len(f"_{i}")]: g[k] for k in g.files if k.endswith(f"_{i}")}
-        logits, u, x = _seeded_case(int(c["seed"]), int(c["B"]), int(c["T"]), float(c["frac"]), float(c["scale"]))
-        if abs(float(logits.double().sum()) - float(c["logits_sum"])) > 1e-6 * max(1.0, abs(float(c["logits_sum"]))):
-            pytest.skip("torch CPU generator stream differs from the one the fixtures were made with")
-        assert np.array_equal(x.numpy(), c["x_t"])
-        yield c, logits, u, x
+from golden_cases import seeded_cases  # noqa: E402
 
 
 def test_sampler_seeded_vectors(golden_dir):
