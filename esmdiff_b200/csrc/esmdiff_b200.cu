@@ -126,29 +126,31 @@ struct ProfScope {
 };
 
 // ------------------------------------------------------------------------------------------------
-// TMA descriptors: bf16 row-major [rows, cols] (cols contiguous), box [box_rows][64 cols], 128B swizzle
+// TMA descriptors: row-major [rows, cols] (cols contiguous), box [box_rows][128 bytes], 128B swizzle
 // ------------------------------------------------------------------------------------------------
 static int get_tmap(esmdiff_ctx* c, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
-                    uint32_t box_rows, CUtensorMap* out) {
-    auto key = std::make_tuple(base, rows, cols * 1000003ull + ld_elems, box_rows, 64u);
+                    uint32_t box_rows, CUtensorMap* out, bool f32 = false) {
+    const uint32_t esz = f32 ? 4 : 2;
+    const uint32_t box_cols = 128 / esz;
+    auto key = std::make_tuple(base, rows, cols * 1000003ull + ld_elems, box_rows, box_cols);
     auto it = c->tmaps.find(key);
     if (it != c->tmaps.end()) {
         *out = it->second;
         return 0;
     }
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {ld_elems * sizeof(bf16)};
-    cuuint32_t box[2] = {64, box_rows};
+    cuuint64_t gstride[1] = {ld_elems * esz};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMap tm;
-    CUresult r = c->encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim,
-                           gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = c->encode(&tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                           const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
-                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+        char buf[200];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu esz=%u base=%p", (int)r,
+                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems, esz, base);
         return c->fail(buf);
     }
     if (c->tmaps.size() > 4096) c->tmaps.clear();
@@ -163,28 +165,41 @@ static int get_tmap(esmdiff_ctx* c, const void* base, uint64_t rows, uint64_t co
 static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, int M, int N, int K,
                        void* out, int64_t ldo, const float* bias, float scale, cudaStream_t st) {
     if (K % gemm::BK != 0 || K <= 0) return c->fail("gemm: K must be a positive multiple of 64");
-    if (epi == gemm::EPI_SWIGLU_BF16 && N % gemm::BN != 0)
-        return c->fail("gemm: SwiGLU epilogue needs N % 256 == 0");
-    CUtensorMap ta, tb;
-    if (get_tmap(c, A, M, K, K, gemm::BM, &ta)) return 1;
-    if (get_tmap(c, W, N, K, K, gemm::BN, &tb)) return 1;
+    if ((epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_RESID_F32) && N % gemm::BN != 0)
+        return c->fail("gemm: SwiGLU / residual epilogues need N % 256 == 0");
+    CUtensorMap ta, tb, tc;
+    if (get_tmap(c, A, M, K, K, gemm::BM_CTA, &ta)) return 1;
+    if (get_tmap(c, W, N, K, K, gemm::BN_CTA, &tb)) return 1;
+    tc = ta;                                     // unused by the direct-store epilogues
+    if (epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_SWIGLU_BF16) {
+        const int out_cols = epi == gemm::EPI_SWIGLU_BF16 ? N / 2 : N;
+        if (ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15))
+            return c->fail("gemm: bf16 output needs a 16-byte aligned base and row stride");
+        if (get_tmap(c, out, M, out_cols, ldo, 32, &tc)) return 1;
+    } else if (epi == gemm::EPI_RESID_F32) {
+        if (ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15))
+            return c->fail("gemm: fp32 residual needs a 16-byte aligned base and row stride");
+        if (get_tmap(c, out, M, N, ldo, 32, &tc, true)) return 1;
+    }
     gemm::Params p;
     p.M = M; p.N = N; p.K = K;
     p.m_tiles = (M + gemm::BM - 1) / gemm::BM;
     p.n_tiles = (N + gemm::BN - 1) / gemm::BN;
     p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
     const int tiles = p.m_tiles * p.n_tiles;
-    const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+    const int max_clusters = c->num_sms / 2;
+    const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
     ProfScope prof(c, epi, 2.0 * M * (double)N * K, st);
 #define LAUNCH_GEMM(E)                                                                         \
     case E: {                                                                                  \
         static bool attr_set = false;                                                          \
         if (!attr_set) {                                                                       \
             CK(cudaFuncSetAttribute(gemm::gemm_bf16_tn_kernel<E>,                              \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES)); \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,               \
+                                    gemm::Cfg<E>::SMEM_BYTES));                                \
             attr_set = true;                                                                   \
         }                                                                                      \
-        gemm::gemm_bf16_tn_kernel<E><<<grid, gemm::THREADS, gemm::SMEM_BYTES, st>>>(ta, tb, p); \
+        gemm::gemm_bf16_tn_kernel<E><<<grid, gemm::THREADS, gemm::Cfg<E>::SMEM_BYTES, st>>>(ta, tb, tc, p); \
         break;                                                                                 \
     }
     switch (epi) {

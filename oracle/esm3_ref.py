@@ -276,6 +276,7 @@ class TimestepEmbedderRef(nn.Module):
     def features(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
         half = dim // 2
         freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=t.dtype) / half)
+        freqs = freqs.to(device=t.device)            # net.py:507-511 does the same
         args = t[:, None] * freqs[None]
         out = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
         if dim % 2:
