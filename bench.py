@@ -4,7 +4,8 @@
 
 One "step" = one complete sampling job of the workload: BASELINE config 2 -- a synthetic L=256
 protein, random-init ESM3-open-sized weights, num_steps=25 (+1 noise-removal forward),
-num_samples=100 in the reference's chunk list [63, 37] (sample_esmdiff.py:181-194).  The timed
+num_samples=100 in ONE batch (the reference splits them [63, 37] only to fit a 32-80 GB GPU,
+sample_esmdiff.py:181-194; `--chunks reference` keeps that list; samples are i.i.d.).  The timed
 window is the reference's own (sample_esmdiff.py:177 -> :223, "Sampling token time").
 structure-tokens/s = num_samples * L / window time.
 
@@ -166,12 +167,12 @@ def cpu_reference(steps: int, warmup: int, budget_s: float, emit_line: bool):
 
 
 def workload_config(chunks=None, n_gpus=1, rng="philox"):
-    from esmdiff_b200.sampling import chunk_sizes
-    chunks = chunks or chunk_sizes(T_TOK, N_SAMPLES)
+    from esmdiff_b200.sampling import chunk_sizes, chunk_sizes_b200
+    chunks = chunks or chunk_sizes_b200(T_TOK, N_SAMPLES)
     return {"workload": "config2: synthetic L=256 protein, random-init ESM3-open dims (d=1536, 48 layers, "
                         "24 heads, V=4101), num_steps=25 + noise removal, num_samples=100 per GPU",
             "L": L_RES, "T": T_TOK, "num_samples_per_gpu": N_SAMPLES, "num_steps": N_STEPS,
-            "chunks": chunks, "uniforms": rng, "parallelism": f"independent samples x{n_gpus}",
+            "chunks": chunks, "reference_chunks": chunk_sizes(T_TOK, N_SAMPLES), "uniforms": rng, "parallelism": f"independent samples x{n_gpus}",
             "l2": "inputs larger than L2 (2.7 GB of bf16 weights streamed per forward)"}
 
 
@@ -183,7 +184,7 @@ def gpu_bench(args):
     from esmdiff_b200.engine import Dims, Engine
     from esmdiff_b200.model import MaskedDiffusionLanguageModeling
     from esmdiff_b200.noise_utils import LogLinearNoise
-    from esmdiff_b200.sampling import chunk_sizes, sample_structure_tokens
+    from esmdiff_b200.sampling import chunk_sizes, chunk_sizes_b200, sample_structure_tokens
     from esmdiff_b200.synthetic import random_state_dict
     from esmdiff_b200.tokenization import synthetic_sequence_tokens
 
@@ -206,7 +207,7 @@ def gpu_bench(args):
 
     model = MaskedDiffusionLanguageModeling(net=Net(), noise_schedule=LogLinearNoise(), sigma_embedder=None,
                                             time_conditioning=True, noise_removal=True, rng=args.rng)
-    chunks = [N_SAMPLES] if args.chunks == "full" else chunk_sizes(T_TOK, N_SAMPLES)
+    chunks = chunk_sizes_b200(T_TOK, N_SAMPLES) if args.chunks == "b200" else chunk_sizes(T_TOK, N_SAMPLES)
     seq_host = synthetic_sequence_tokens(L_RES, seed=0).pin_memory()
     seq_dev = seq_host.to(dev)
     sigma, mc_t, mc_s = model._schedule(N_STEPS, EPS, 1.0, dev)
@@ -325,8 +326,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunks", default="reference", choices=["reference", "full"],
-                    help="reference: sample_esmdiff.py chunk list [63, 37]; full: one batch of 100")
+    ap.add_argument("--chunks", default="b200", choices=["b200", "reference"],
+                    help="b200: batch list sized for 180 GB (one batch of 100 here); reference: the "
+                         "reference's 32-80 GB-GPU memory guard, sample_esmdiff.py:181-194 -> [63, 37]")
     ap.add_argument("--rng", default="philox", choices=["philox", "torch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

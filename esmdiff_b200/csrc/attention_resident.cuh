@@ -1,0 +1,315 @@
+// Non-causal multi-head attention, d_head = 64, with the K and V of one (sample, head) RESIDENT in
+// shared memory: the variant for the sequence lengths the sampling path is quoted on
+// (T = L + 2 <= 766; T = 258 keeps two CTAs per SM).  Replaces F.scaled_dot_product_attention on
+// the reference path (esm MultiHeadAttention.forward with seq_id None).
+//
+// One CTA = one (sample b, head h); it walks ALL query tiles of 128 rows, so K/V are read from
+// L2/HBM once per (b, h) instead of once per query tile.  Per step (query tile qt, kv tile j):
+//   MMA warp  : S = Q_qt K_j^T     UMMA 128 x ncols x 16 (x4), fp32 into one of two TMEM S buffers,
+//               issued two steps ahead of the softmax
+//               O (+)= P V_j       UMMA with A = P FROM TMEM (bf16 pairs written over the S buffer
+//               l (+)= P 1          by the softmax threads), B = V_j as MN-major smem operand; the
+//                                  row sums come from a second, N = 16 MMA against a tile of ones,
+//                                  so the denominator uses exactly the rounded P of the numerator
+//   4 softmax warps (thread = query row = TMEM lane): row max of the tile; the running max is only
+//               raised when the tile max exceeds it by more than 2^8 (then O and l are rescaled in
+//               TMEM -- rare after the first tile), p = exp2(s*scale - m), packed to bf16 and
+//               stored back to TMEM.  No shared-memory round trip for P, no per-tile read of O.
+//   The last kv tile is only as wide as needed (multiple of 16 columns): T = 258 costs 4 x 64 + 16
+//   columns, not 5 x 64.  Warps whose 32 query rows are all >= T skip the softmax (the 2-row tail
+//   tile of T = 258 keeps one warp busy, not four).
+// Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64; q,k already LayerNormed + RoPE'd)
+// Output ctx : bf16 [M, D]
+#pragma once
+#include "ptx.cuh"
+
+namespace esmdiff {
+namespace attn2 {
+
+constexpr int BQ = 128;
+constexpr int BKV = 64;
+constexpr int DH = 64;
+constexpr int MAX_KV_TILES = 12;            // T <= 768
+constexpr int Q_BYTES = BQ * DH * 2;        // 16 KiB
+constexpr int KV_TILE_BYTES = BKV * DH * 2; // 8 KiB
+constexpr int ONES_BYTES = 16 * 128;        // [16 n][64 k] bf16 ones, one 128-byte row per n
+constexpr int BAR_BYTES = 512;
+constexpr int THREADS = 192;                // warps 0-3 softmax, 4 TMA, 5 MMA
+constexpr int TMEM_COLS = 256;              // S0 [0,64) S1 [64,128) O [128,192) l [192,208)
+constexpr int COL_O = 128;
+constexpr int COL_L = 192;
+constexpr float RESCALE_LOG2 = 8.0f;        // lazy rescale threshold: p <= 2^8
+
+struct Params {
+    int B, T, H;
+    int nq;                     // ceil(T / 128)
+    int nkv;                    // ceil(T / 64)
+    int tail_cols;              // width of the last kv tile: multiple of 16 in [16, 64]
+    __nv_bfloat16* ctx;         // [B*T, H*64]
+    float scale_log2;           // (1/sqrt(64)) * log2(e)
+};
+
+__host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
+    return (nkv - 1) * KV_TILE_BYTES + tail_cols * 128;
+}
+__host__ inline int smem_bytes(int nkv, int tail_cols) {
+    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + ONES_BYTES + BAR_BYTES;
+}
+
+__global__ void __launch_bounds__(THREADS, 2)
+attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [128 rows][64 cols]
+                          const __grid_constant__ CUtensorMap tmKV,     // box [ 64 rows][64 cols]
+                          const __grid_constant__ CUtensorMap tmKVt,    // box [tail rows][64 cols]
+                          const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int kvb = kv_bytes(p.nkv, p.tail_cols);
+    uint8_t* sQ = smem;                                   // two query-tile buffers
+    uint8_t* sK = sQ + 2 * Q_BYTES;
+    uint8_t* sV = sK + kvb;
+    uint8_t* sOnes = sV + kvb;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
+    uint64_t* q_full = bars;                              // [2]
+    uint64_t* q_empty = bars + 2;                         // [2]
+    uint64_t* s_full = bars + 4;                          // [2]  MMA -> softmax
+    uint64_t* p_full = bars + 6;                          // [2]  softmax (128 threads) -> MMA
+    uint64_t* pv_done = bars + 8;                         // 1    completes once per step
+    uint64_t* o_free = bars + 9;                          // 1    completes once per query tile
+    uint64_t* o_full = bars + 10;                         // 1    last PV of a query tile retired
+    uint64_t* k_full = bars + 11;                         // [MAX_KV_TILES], single use
+    uint64_t* v_full = k_full + MAX_KV_TILES;             // [MAX_KV_TILES], single use
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_full + MAX_KV_TILES);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int h = blockIdx.x % p.H;
+    const int b = blockIdx.x / p.H;
+    const int D = p.H * DH;
+    const int row0 = b * p.T;
+    const int nq = p.nq, nkv = p.nkv;
+    const int nsteps = nq * nkv;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmKV);
+        tma_prefetch_desc(&tmKVt);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&q_full[s], 1);
+            mbar_init(&q_empty[s], 1);
+            mbar_init(&s_full[s], 1);
+            mbar_init(&p_full[s], 128);
+        }
+        mbar_init(pv_done, 1);
+        mbar_init(o_free, 128);
+        mbar_init(o_full, 1);
+        for (int j = 0; j < nkv; ++j) {
+            mbar_init(&k_full[j], 1);
+            mbar_init(&v_full[j], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    if (warp < 4) {
+        reinterpret_cast<uint4*>(sOnes)[threadIdx.x] =
+            make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);     // bf16 1.0 pairs
+        fence_proxy_async_smem();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            auto load_q = [&](int qt) {
+                uint64_t* bar = &q_full[qt & 1];
+                mbar_arrive_expect_tx(bar, Q_BYTES);
+                tma_load_2d(sQ + (qt & 1) * Q_BYTES, &tmQ, bar, h * DH, row0 + qt * BQ);
+            };
+            auto load_kv = [&](uint8_t* dst, uint64_t* bar, int col, int j) {
+                const bool last = j == nkv - 1;
+                mbar_arrive_expect_tx(bar, last ? p.tail_cols * 128 : KV_TILE_BYTES);
+                tma_load_2d(dst + j * KV_TILE_BYTES, last ? &tmKVt : &tmKV, bar, col, row0 + j * BKV);
+            };
+            load_q(0);
+            for (int j = 0; j < nkv; ++j) load_kv(sK, &k_full[j], D + h * DH, j);
+            if (nq > 1) load_q(1);
+            for (int j = 0; j < nkv; ++j) load_kv(sV, &v_full[j], 2 * D + h * DH, j);
+            for (int qt = 2; qt < nq; ++qt) {
+                mbar_wait(&q_empty[qt & 1], ((qt >> 1) - 1) & 1);
+                load_q(qt);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, DH, 1);   // P V : V is MN-major
+            constexpr uint32_t idesc_l = umma_idesc_bf16(BQ, 16, 0);    // P 1 : ones tile K-major
+            const uint64_t onesdesc = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
+            const uint32_t tmem_o = tmem_base + COL_O;
+            const uint32_t tmem_l = tmem_base + COL_L;
+            auto issue_s = [&](int i) {
+                const int qt = i / nkv, j = i - qt * nkv;
+                if (j == 0) mbar_wait(&q_full[qt & 1], (qt >> 1) & 1);
+                if (qt == 0) mbar_wait(&k_full[j], 0);
+                tcgen05_fence_after();
+                const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (qt & 1) * Q_BYTES), 16, 1024);
+                const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + j * KV_TILE_BYTES), 16, 1024);
+                const uint32_t idesc = umma_idesc_bf16(BQ, j == nkv - 1 ? p.tail_cols : BKV, 0);
+#pragma unroll
+                for (int k = 0; k < DH / 16; ++k)
+                    umma_bf16_ss(tmem_base + (i & 1) * BKV, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+                umma_commit(&s_full[i & 1]);
+                if (j == nkv - 1) umma_commit(&q_empty[qt & 1]);
+            };
+            issue_s(0);
+            if (nsteps > 1) issue_s(1);
+            for (int i = 0; i < nsteps; ++i) {
+                const int qt = i / nkv, j = i - qt * nkv;
+                if (qt == 0) mbar_wait(&v_full[j], 0);
+                mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+                if (j == 0 && qt > 0) mbar_wait(o_free, (qt - 1) & 1);
+                tcgen05_fence_after();
+                // V tile [kv rows][64 d] is an MN-major B operand: 128-byte rows along N = d,
+                // 8-row (k) groups 1024 B apart; one UMMA K-step (16 kv rows) = 2048 B.
+                const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + j * KV_TILE_BYTES), 16, 1024);
+                const uint32_t tp = tmem_base + (i & 1) * BKV;          // P: bf16 pairs, 8 columns per K-step
+                const int ksteps = (j == nkv - 1 ? p.tail_cols : BKV) / 16;
+                for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t acc = (j | k) != 0 ? 1u : 0u;
+                    umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, acc);
+                    umma_bf16_ts(tmem_l, tp + 8 * k, onesdesc, idesc_l, acc);
+                }
+                umma_commit(pv_done);
+                if (j == nkv - 1) umma_commit(o_full);
+                if (i + 2 < nsteps) issue_s(i + 2);       // overwrites P_i's buffer: ordered after PV_i
+            }
+        }
+    } else {
+        // ===================== softmax / output warps: thread = query row =====================
+        const int r = threadIdx.x;                                   // 0..127 == TMEM lane
+        const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+        const uint32_t t_o = tmem_base + lane_addr + COL_O;
+        const float sc = p.scale_log2;
+        const float thresh = RESCALE_LOG2 / sc;
+
+        // out[row] = O / l for query tile qt (after its last PV has retired), then free O
+        auto epilogue = [&](int qt) {
+            mbar_wait(o_full, qt & 1);
+            tcgen05_fence_after();
+            if (qt * BQ + warp * 32 < p.T) {
+                const float inv = 1.0f / __uint_as_float(tmem_ld_32x32b_x1(tmem_base + lane_addr + COL_L));
+                const int t = qt * BQ + r;
+                uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<long long>(row0 + t) * D + h * DH);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t o[16];
+                    tmem_ld_32x32b_x16(t_o + c * 16, o);
+                    tmem_ld_wait();
+                    if (t < p.T) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g)
+                            dst[c * 2 + g] = make_uint4(
+                                pack_bf16x2(__uint_as_float(o[8 * g]) * inv, __uint_as_float(o[8 * g + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv, __uint_as_float(o[8 * g + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv, __uint_as_float(o[8 * g + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv, __uint_as_float(o[8 * g + 7]) * inv));
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            mbar_arrive(o_free);
+        };
+
+        float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
+        for (int qt = 0; qt < nq; ++qt) {
+            const bool active = qt * BQ + warp * 32 < p.T;           // warp-uniform
+            for (int j = 0; j < nkv; ++j) {
+                const int i = qt * nkv + j;
+                const uint32_t t_s = tmem_base + lane_addr + (i & 1) * BKV;
+                mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+                tcgen05_fence_after();
+                if (active) {
+                    const bool last = j == nkv - 1;
+                    const int nch = (last ? p.tail_cols : BKV) >> 4;     // 16-column chunks
+                    uint32_t s[64];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nch) tmem_ld_32x32b_x16(t_s + c * 16, s + c * 16);
+                    tmem_ld_wait();
+                    float mx = -INFINITY;
+                    if (last) {
+                        const int valid = p.T - j * BKV;             // >= 1 valid kv columns in this tile
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < nch) {
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) {
+                                    const float a = (c * 16 + e < valid) ? __uint_as_float(s[c * 16 + e]) : -INFINITY;
+                                    s[c * 16 + e] = __float_as_uint(a);
+                                    mx = fmaxf(mx, a);
+                                }
+                            }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(s[e]));
+                    }
+                    if (j == 0) {
+                        m_run = mx;
+                    } else {
+                        const bool need = mx > m_run + thresh;
+                        if (__any_sync(0xffffffffu, need)) {
+                            // raise the running max: rescale O and l in TMEM once PV_{i-1} has retired
+                            const float m_new = need ? mx : m_run;
+                            const float f = fast_exp2((m_run - m_new) * sc);
+                            mbar_wait(pv_done, (i - 1) & 1);
+                            tcgen05_fence_after();
+#pragma unroll 1
+                            for (int c = 0; c < 5; ++c) {            // O: 4 chunks, l: 1 chunk (contiguous)
+                                uint32_t o[16];
+                                tmem_ld_32x32b_x16(t_o + c * 16, o);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * f);
+                                tmem_st_32x32b_x16(t_o + c * 16, o);
+                            }
+                            tmem_st_wait();
+                            m_run = m_new;
+                        }
+                    }
+                    const float nm = -m_run * sc;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nch) {
+                            uint32_t pk[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                pk[e] = pack_bf16x2(fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e]), sc, nm)),
+                                                    fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e + 1]), sc, nm)));
+                            tmem_st_32x32b_x8(t_s + c * 8, pk);      // P over the S buffer: 2 bf16 per column
+                        }
+                    tmem_st_wait();
+                }
+                tcgen05_fence_before();
+                mbar_arrive(&p_full[i & 1]);
+                if (j == 0 && qt > 0) epilogue(qt - 1);    // deferred: overlaps PV of the previous tile
+            }
+        }
+        epilogue(nq - 1);
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace attn2
+}  // namespace esmdiff

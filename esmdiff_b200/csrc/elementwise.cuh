@@ -93,7 +93,16 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
         sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w;
         sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
     }
-#pragma unroll 1
+    // both rows (q and k) are requested before either is reduced: 12 x 16 B in flight per lane
+    uint4 raw[2][MAXC];
+#pragma unroll
+    for (int which = 0; which < 2; ++which)
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+            if (i < nc)
+                raw[which][i] = *reinterpret_cast<const uint4*>(
+                    qkv + static_cast<long long>(row) * 3 * D + which * D + i * 256 + lane * 8);
+#pragma unroll
     for (int which = 0; which < 2; ++which) {
         __nv_bfloat16* base = qkv + static_cast<long long>(row) * 3 * D + which * D;
         const float* w = which == 0 ? q_w : k_w;
@@ -102,8 +111,7 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
 #pragma unroll
         for (int i = 0; i < MAXC; ++i)
             if (i < nc) {
-                const uint4 raw = *reinterpret_cast<const uint4*>(base + i * 256 + lane * 8);
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[which][i]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float2 f = __bfloat1622float2(h2[e]);

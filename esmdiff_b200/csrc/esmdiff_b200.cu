@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -15,6 +16,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_resident.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -50,6 +52,8 @@ struct esmdiff_ctx {
     int num_sms = 148;
     std::string err;
     int64_t launches = 0;
+    int gemm_bn = 0;           // 0 = choose per shape, 192 / 256 = force (ESMDIFF_GEMM_BN; tuning only)
+    int attn_variant = 0;      // 0 = resident K/V where it fits, 1 = always the streaming kernel (ESMDIFF_ATTN=stream)
     EncodeTiledFn encode = nullptr;
 
     std::vector<LayerW> layers;
@@ -165,11 +169,22 @@ static int get_tmap(esmdiff_ctx* c, const void* base, uint64_t rows, uint64_t co
 static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, int M, int N, int K,
                        void* out, int64_t ldo, const float* bias, float scale, cudaStream_t st) {
     if (K % gemm::BK != 0 || K <= 0) return c->fail("gemm: K must be a positive multiple of 64");
-    if ((epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_RESID_F32) && N % gemm::BN != 0)
-        return c->fail("gemm: SwiGLU / residual epilogues need N % 256 == 0");
+    const int max_clusters = c->num_sms / 2;
+    const int m_tiles = (M + gemm::BM - 1) / gemm::BM;
+    // tile width: 256, or 192 for the residual epilogue when that wastes less of the last wave
+    int BN = 256;
+    if (epi == gemm::EPI_RESID_F32 && N % 192 == 0 && c->gemm_bn != 256) {
+        auto cost = [&](int bn) {
+            const int64_t tiles = (int64_t)m_tiles * ((N + bn - 1) / bn);
+            return (tiles + max_clusters - 1) / max_clusters * bn;
+        };
+        if (c->gemm_bn == 192 || N % 256 != 0 || cost(192) < cost(256)) BN = 192;
+    }
+    if ((epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_RESID_F32) && N % BN != 0)
+        return c->fail("gemm: SwiGLU / residual epilogues need N % 256 == 0 (residual: or N % 192 == 0)");
     CUtensorMap ta, tb, tc;
     if (get_tmap(c, A, M, K, K, gemm::BM_CTA, &ta)) return 1;
-    if (get_tmap(c, W, N, K, K, gemm::BN_CTA, &tb)) return 1;
+    if (get_tmap(c, W, N, K, K, BN / 2, &tb)) return 1;
     tc = ta;                                     // unused by the direct-store epilogues
     if (epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_SWIGLU_BF16) {
         const int out_cols = epi == gemm::EPI_SWIGLU_BF16 ? N / 2 : N;
@@ -183,31 +198,32 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     }
     gemm::Params p;
     p.M = M; p.N = N; p.K = K;
-    p.m_tiles = (M + gemm::BM - 1) / gemm::BM;
-    p.n_tiles = (N + gemm::BN - 1) / gemm::BN;
+    p.m_tiles = m_tiles;
+    p.n_tiles = (N + BN - 1) / BN;
     p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
     const int tiles = p.m_tiles * p.n_tiles;
-    const int max_clusters = c->num_sms / 2;
     const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
     ProfScope prof(c, epi, 2.0 * M * (double)N * K, st);
-#define LAUNCH_GEMM(E)                                                                         \
-    case E: {                                                                                  \
+#define LAUNCH_GEMM(E, BNV)                                                                    \
+    {                                                                                          \
         static bool attr_set = false;                                                          \
         if (!attr_set) {                                                                       \
-            CK(cudaFuncSetAttribute(gemm::gemm_bf16_tn_kernel<E>,                              \
+            CK(cudaFuncSetAttribute(gemm::gemm_bf16_tn_kernel<E, BNV>,                         \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,               \
-                                    gemm::Cfg<E>::SMEM_BYTES));                                \
+                                    gemm::Cfg<E, BNV>::SMEM_BYTES));                           \
             attr_set = true;                                                                   \
         }                                                                                      \
-        gemm::gemm_bf16_tn_kernel<E><<<grid, gemm::THREADS, gemm::Cfg<E>::SMEM_BYTES, st>>>(ta, tb, tc, p); \
-        break;                                                                                 \
+        gemm::gemm_bf16_tn_kernel<E, BNV><<<grid, gemm::THREADS, gemm::Cfg<E, BNV>::SMEM_BYTES, st>>>(ta, tb, tc, p); \
     }
     switch (epi) {
-        LAUNCH_GEMM(gemm::EPI_STORE_BF16)
-        LAUNCH_GEMM(gemm::EPI_RESID_F32)
-        LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16)
-        LAUNCH_GEMM(gemm::EPI_BIAS_GELU_F32)
-        LAUNCH_GEMM(gemm::EPI_BIAS_F32)
+        case gemm::EPI_STORE_BF16: LAUNCH_GEMM(gemm::EPI_STORE_BF16, 256) break;
+        case gemm::EPI_RESID_F32:
+            if (BN == 192) LAUNCH_GEMM(gemm::EPI_RESID_F32, 192)
+            else LAUNCH_GEMM(gemm::EPI_RESID_F32, 256)
+            break;
+        case gemm::EPI_SWIGLU_BF16: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16, 256) break;
+        case gemm::EPI_BIAS_GELU_F32: LAUNCH_GEMM(gemm::EPI_BIAS_GELU_F32, 256) break;
+        case gemm::EPI_BIAS_F32: LAUNCH_GEMM(gemm::EPI_BIAS_F32, 256) break;
         default: return c->fail("gemm: unknown epilogue");
     }
 #undef LAUNCH_GEMM
@@ -259,7 +275,8 @@ static int launch_qk_norm_rope(esmdiff_ctx* c, bf16* qkv, const float* qw, const
     return 0;
 }
 
-static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H, cudaStream_t st) {
+static int launch_attention_streaming(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H,
+                                      cudaStream_t st) {
     const int D = H * attn::DH;
     const int64_t M = (int64_t)B * T;
     CUtensorMap tq, tkv;
@@ -279,6 +296,39 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     const int grid = B * H * p.q_tiles;
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn::DH, st);
     attn::attention_fwd_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tq, tkv, p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// K/V of one (sample, head) resident in shared memory: every T whose K and V fit beside two query
+// buffers (T <= 766); longer sequences stream K/V tiles (attention.cuh).
+static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H, cudaStream_t st) {
+    const int nkv = (T + attn2::BKV - 1) / attn2::BKV;
+    const int tail_cols = ((T - (nkv - 1) * attn2::BKV) + 15) / 16 * 16;
+    const int smem = attn2::smem_bytes(nkv, tail_cols);
+    if (c->attn_variant == 1 || nkv > attn2::MAX_KV_TILES || smem > 227 * 1024)
+        return launch_attention_streaming(c, qkv, out, B, T, H, st);
+    const int D = H * attn2::DH;
+    const int64_t M = (int64_t)B * T;
+    CUtensorMap tq, tkv, tkvt;
+    if (get_tmap(c, qkv, M, 3 * D, 3 * D, attn2::BQ, &tq)) return 1;
+    if (get_tmap(c, qkv, M, 3 * D, 3 * D, attn2::BKV, &tkv)) return 1;
+    if (get_tmap(c, qkv, M, 3 * D, 3 * D, tail_cols, &tkvt)) return 1;
+    attn2::Params p;
+    p.B = B; p.T = T; p.H = H;
+    p.nq = (T + attn2::BQ - 1) / attn2::BQ;
+    p.nkv = nkv;
+    p.tail_cols = tail_cols;
+    p.ctx = out;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        CK(cudaFuncSetAttribute(attn2::attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn2::DH, st);
+    attn2::attention_resident_kernel<<<B * H, attn2::THREADS, smem, st>>>(tq, tkv, tkvt, p);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -521,6 +571,8 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->layers.resize(cfg->n_layers);
+    if (const char* e = getenv("ESMDIFF_GEMM_BN")) c->gemm_bn = atoi(e);
+    if (const char* e = getenv("ESMDIFF_ATTN")) c->attn_variant = strcmp(e, "stream") == 0 ? 1 : 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);

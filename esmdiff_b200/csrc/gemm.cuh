@@ -23,14 +23,14 @@ namespace gemm {
 
 constexpr int BM = 256;                   // rows per CTA pair
 constexpr int BM_CTA = 128;               // rows per CTA (= TMEM lanes)
-constexpr int BN = 256;
-constexpr int BN_CTA = 128;               // W rows each CTA loads
+constexpr int BN_MAX = 256;               // tile width is a template parameter: 256, or 192 for the
+                                          // N = 1536 GEMMs (6 -> 8 column tiles: 512 tiles over 74
+                                          // CTA pairs = 6.92 waves instead of 5.19 -> 6)
 constexpr int BK = 64;                    // 64 bf16 = one 128-byte swizzle row
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM_CTA * BK * 2;  // 16 KiB
-constexpr int B_BYTES = BN_CTA * BK * 2;  // 16 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 2 * BN;         // two fp32 accumulator stages = all 512 columns
+constexpr int TMEM_COLS = 512;            // two fp32 accumulator stages, 256 columns apart
+constexpr int ACC_STRIDE = 256;
 constexpr int EPI_WARPS = 8;              // warp w: TMEM lane quarter w % 4, column half (w - 4) / 4
 constexpr int BOX_BYTES = 4096;           // one 32-row x 128-byte staging box
 constexpr int THREADS = 384;              // w0 TMA, w1 MMA (leader CTA), w2 TMEM alloc, w3 idle, w4-11 epilogue
@@ -45,17 +45,23 @@ enum Epilogue {
 
 // The residual epilogue double-buffers its x boxes (TMA load -> add -> TMA store), paid for with
 // one pipeline stage.
-template <int EPI> struct Cfg {
+template <int EPI, int BN> struct Cfg {
+    static_assert(BN == 256 || BN == 192, "tile widths instantiated");
+    static_assert(BN == 256 || EPI == EPI_RESID_F32, "BN = 192 only with the 32-column residual epilogue");
+    static constexpr int BN_CTA = BN / 2;                 // W rows each CTA loads
+    static constexpr int B_BYTES = BN_CTA * BK * 2;       // 16 / 12 KiB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BOXES = EPI == EPI_RESID_F32 ? 2 : 1;
-    static constexpr int STAGES = EPI == EPI_RESID_F32 ? 5 : 6;
     static constexpr int STG_BYTES = EPI_WARPS * BOXES * BOX_BYTES;
+    static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STG_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT < MAX_STAGES ? STAGES_FIT : MAX_STAGES;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + 512;
-    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(SMEM_BYTES <= 227 * 1024 && STAGES >= 4, "shared memory budget");
 };
 
 struct Params {
     int M, N, K;          // N = rows of W actually present (TMA zero-fills beyond)
-    int m_tiles, n_tiles; // tiles of 256 x 256
+    int m_tiles, n_tiles; // tiles of 256 x BN
     void* out;            // direct-store epilogues (3, 4): fp32
     long long ldo;        // elements between output rows
     const float* bias;    // [N] or null
@@ -75,19 +81,22 @@ __device__ __forceinline__ void st_swz16(uint8_t* box, int row, int chunk, uint3
     *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(a, b, c, d);
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] bf16, box 128 x 64
                     const __grid_constant__ CUtensorMap tmB,     // W   [N, K] bf16, box 128 x 64
                     const __grid_constant__ CUtensorMap tmC,     // out: bf16 box 32 x 64 / fp32 box 32 x 32
                     const Params p) {
-    constexpr int STAGES = Cfg<EPI>::STAGES;
-    constexpr int BOXES = Cfg<EPI>::BOXES;
+    using C = Cfg<EPI, BN>;
+    constexpr int STAGES = C::STAGES;
+    constexpr int BOXES = C::BOXES;
+    constexpr int BN_CTA = C::BN_CTA;
+    constexpr int STAGE_BYTES = C::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* stg_all = smem + STAGES * STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + Cfg<EPI>::STG_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + C::STG_BYTES);
     uint64_t* full = bars;                 // [STAGES]  TMA (both CTAs) -> MMA; used in the leader only
     uint64_t* empty = bars + MAX_STAGES;   // [STAGES]  MMA -> TMA, multicast to both CTAs
     uint64_t* tfull = bars + 2 * MAX_STAGES;   // [2]   MMA -> epilogue, multicast to both CTAs
@@ -159,7 +168,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tcgen05_fence_after();
@@ -191,7 +200,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             const int nb = tile % p.n_tiles;
             const int n0 = nb * BN + half * (BN / 2);
             const int row_base = (tile / p.n_tiles) * BM + rank * BM_CTA + q * 32;
-            const uint32_t t_row = tmem_base + acc * BN + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t t_row = tmem_base + acc * ACC_STRIDE + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
 
             if constexpr (EPI == EPI_STORE_BF16) {
                 mbar_wait(&tfull[acc], acc_phase);
@@ -229,7 +238,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 // this warp produces output columns [64 half, 64 half + 64) of the tile's 128
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
-                const uint32_t t_gate = tmem_base + acc * BN + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
+                const uint32_t t_gate = tmem_base + acc * ACC_STRIDE + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
                 if (lane == 0) bulk_wait_group_read<0>();
                 __syncwarp();
 #pragma unroll

@@ -28,6 +28,22 @@ def chunk_sizes(T: int, num_samples: int, n_max_residue_square: int = N_MAX_RESI
     return bsz
 
 
+MAX_TOKENS_PER_BATCH = 1 << 18              # B*T rows per ddpm_sample call on a 180 GB B200
+
+
+def chunk_sizes_b200(T: int, num_samples: int, max_tokens: int = MAX_TOKENS_PER_BATCH) -> list[int]:
+    """Batch list sized for 180 GB of HBM instead of the reference's ``B*T^2 <= 4.2M`` guard (a
+    32-80 GB-GPU memory heuristic): all samples of a target in one batch while B*T stays below
+    ``max_tokens`` (2^18 rows = 4.3 GB of fp32 logits + ~3 GB of activations), else equal chunks.
+    Samples are i.i.d. given the sequence, so the chunking does not change what is sampled; it
+    only changes how a *torch* uniform stream would be consumed, which is why the torch-RNG
+    parity mode keeps :func:`chunk_sizes`."""
+    per = max(1, max_tokens // T)
+    n_chunks = -(-num_samples // per)
+    base, rem = divmod(num_samples, n_chunks)
+    return [base + (1 if i < rem else 0) for i in range(n_chunks)]
+
+
 def build_prior(structure_tokens: torch.Tensor, batch: int, mask_ids=None, filled_ids=None,
                 total_size=None):
     """``input_prior`` (sample_esmdiff.py:197-209).  ``mask_ids`` index TOKEN positions (BOS = 0),
@@ -54,7 +70,12 @@ def sample_structure_tokens(model, sequence_tokens_singleton: torch.Tensor, num_
     """Returns (tokens int64 (num_samples, L) without BOS/EOS, seconds) -- the metric's window."""
     T = sequence_tokens_singleton.size(0)
     start_t = time()
-    bsz = chunks if chunks is not None else chunk_sizes(T, num_samples)
+    if chunks is None:
+        # torch-RNG parity mode consumes the uniform stream chunk by chunk exactly like the
+        # reference; the library-Philox mode is chunking-independent and batches for the B200
+        chunks = (chunk_sizes(T, num_samples) if getattr(model, "rng", "torch") == "torch"
+                  else chunk_sizes_b200(T, num_samples))
+    bsz = chunks
     if verbose:
         print(f"Total {num_samples} samples will be generated in batchs {bsz}...")
     outs = []

@@ -1,0 +1,36 @@
+"""Launch each hot kernel a few times at the config-2 shape so `ncu --set full -k regex:...` can
+capture it in seconds (never profile the whole bench under --set full)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from esmdiff_b200.engine import Dims, Engine  # noqa: E402
+
+dev = torch.device("cuda")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+T, H = 258, 24
+M = B * T
+g = torch.Generator(device="cuda").manual_seed(0)
+e = Engine(Dims())
+a = torch.randn(M, 1536, device=dev, generator=g).bfloat16()
+hb = torch.randn(M, 4096, device=dev, generator=g).bfloat16()
+wq = (torch.randn(4608, 1536, device=dev, generator=g) / 39).bfloat16()
+wo = (torch.randn(1536, 1536, device=dev, generator=g) / 39).bfloat16()
+w1 = (torch.randn(8192, 1536, device=dev, generator=g) / 39).bfloat16()
+w2 = (torch.randn(1536, 4096, device=dev, generator=g) / 64).bfloat16()
+x = torch.randn(M, 1536, device=dev, generator=g)
+qkv = torch.empty(M, 4608, dtype=torch.bfloat16, device=dev)
+h = torch.empty(M, 4096, dtype=torch.bfloat16, device=dev)
+ones = torch.ones(1536, device=dev)
+for _ in range(3):
+    xn = e.op_layernorm(x, ones, ones)
+    e.op_gemm(0, xn, wq, qkv)
+    e.op_qk_norm_rope(qkv, ones, ones, B, T)
+    att = e.op_attention(qkv, B, T, H)
+    e.op_gemm(1, att, wo, x, scale=1.1547)
+    e.op_gemm(2, xn, w1, h)
+    e.op_gemm(1, hb, w2, x, scale=1.1547)
+e.synchronize()
+print("done", e.launch_count)
