@@ -8,13 +8,12 @@
 //   MMA warp  : S = Q_qt K_j^T     UMMA 128 x ncols x 16 (x4), fp32 into one of two TMEM S buffers,
 //               issued two steps ahead of the softmax
 //               O (+)= P V_j       UMMA with A = P FROM TMEM (bf16 pairs written over the S buffer
-//               l (+)= P 1          by the softmax threads), B = V_j as MN-major smem operand; the
-//                                  row sums come from a second, N = 16 MMA against a tile of ones,
-//                                  so the denominator uses exactly the rounded P of the numerator
+//                                  by the softmax threads), B = V_j as MN-major smem operand
 //   4 softmax warps (thread = query row = TMEM lane): row max of the tile; the running max is only
-//               raised when the tile max exceeds it by more than 2^8 (then O and l are rescaled in
-//               TMEM -- rare after the first tile), p = exp2(s*scale - m), packed to bf16 and
-//               stored back to TMEM.  No shared-memory round trip for P, no per-tile read of O.
+//               raised when the tile max exceeds it by more than 2^8 (then O is rescaled in TMEM and
+//               the row sum in its register -- rare after the first tile), p = exp2(s*scale - m),
+//               packed to bf16 and stored back to TMEM.  No shared-memory round trip for P, no
+//               per-tile read of O.
 //   The last kv tile is only as wide as needed (multiple of 16 columns): T = 258 costs 4 x 64 + 16
 //   columns, not 5 x 64.  Warps whose 32 query rows are all >= T skip the softmax (the 2-row tail
 //   tile of T = 258 keeps one warp busy, not four).
@@ -32,12 +31,10 @@ constexpr int DH = 64;
 constexpr int MAX_KV_TILES = 12;            // T <= 768
 constexpr int Q_BYTES = BQ * DH * 2;        // 16 KiB
 constexpr int KV_TILE_BYTES = BKV * DH * 2; // 8 KiB
-constexpr int ONES_BYTES = 16 * 128;        // [16 n][64 k] bf16 ones, one 128-byte row per n
 constexpr int BAR_BYTES = 512;
 constexpr int THREADS = 192;                // warps 0-3 softmax, 4 TMA, 5 MMA
-constexpr int TMEM_COLS = 256;              // S0 [0,64) S1 [64,128) O [128,192) l [192,208)
+constexpr int TMEM_COLS = 256;              // S0 [0,64) S1 [64,128) O [128,192)
 constexpr int COL_O = 128;
-constexpr int COL_L = 192;
 constexpr float RESCALE_LOG2 = 8.0f;        // lazy rescale threshold: p <= 2^8
 
 struct Params {
@@ -53,7 +50,7 @@ __host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
     return (nkv - 1) * KV_TILE_BYTES + tail_cols * 128;
 }
 __host__ inline int smem_bytes(int nkv, int tail_cols) {
-    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + ONES_BYTES + BAR_BYTES;
+    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + BAR_BYTES;
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -68,8 +65,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint8_t* sQ = smem;                                   // two query-tile buffers
     uint8_t* sK = sQ + 2 * Q_BYTES;
     uint8_t* sV = sK + kvb;
-    uint8_t* sOnes = sV + kvb;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + ONES_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kvb);
     uint64_t* q_full = bars;                              // [2]
     uint64_t* q_empty = bars + 2;                         // [2]
     uint64_t* s_full = bars + 4;                          // [2]  MMA -> softmax
@@ -113,11 +109,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
-    if (warp < 4) {
-        reinterpret_cast<uint4*>(sOnes)[threadIdx.x] =
-            make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);     // bf16 1.0 pairs
-        fence_proxy_async_smem();
-    }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -147,47 +138,67 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, DH, 1);   // P V : V is MN-major
-            constexpr uint32_t idesc_l = umma_idesc_bf16(BQ, 16, 0);    // P 1 : ones tile K-major
-            const uint64_t onesdesc = umma_desc_sw128(smem_u32(sOnes), 16, 1024);
-            const uint32_t tmem_o = tmem_base + COL_O;
-            const uint32_t tmem_l = tmem_base + COL_L;
-            auto issue_s = [&](int i) {
-                const int qt = i / nkv, j = i - qt * nkv;
-                if (j == 0) mbar_wait(&q_full[qt & 1], (qt >> 1) & 1);
-                if (qt == 0) mbar_wait(&k_full[j], 0);
-                tcgen05_fence_after();
-                const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (qt & 1) * Q_BYTES), 16, 1024);
-                const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + j * KV_TILE_BYTES), 16, 1024);
-                const uint32_t idesc = umma_idesc_bf16(BQ, j == nkv - 1 ? p.tail_cols : BKV, 0);
+        // The whole warp walks the schedule (warp-uniform control flow: counters and descriptors
+        // stay in uniform registers); one elected lane issues the tcgen05 instructions.  The
+        // first cut did this from a single thread with per-step integer divisions and took
+        // ~2.5k cycles per step -- the issuing thread, not MUFU or the tensor pipe, was the
+        // bottleneck (ncu r1c: softmax warps 33 % stalled on s_full).
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, DH, 1);       // P V : V is MN-major
+        const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, 0);
+        const uint32_t idesc_s_tail = umma_idesc_bf16(BQ, p.tail_cols, 0);
+        const uint64_t desc_q0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t desc_k0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+        const uint64_t desc_v0 = umma_desc_sw128(smem_u32(sV), 16, 1024);
+        const uint32_t tmem_o = tmem_base + COL_O;
+        int s_i = 0, s_qt = 0, s_j = 0;                                 // next S = Q K^T to issue
+        auto issue_s = [&]() {
+            if (s_j == 0) mbar_wait(&q_full[s_qt & 1], (s_qt >> 1) & 1);
+            if (s_qt == 0) mbar_wait(&k_full[s_j], 0);
+            tcgen05_fence_after();
+            const uint64_t qdesc = desc_q0 + static_cast<uint64_t>((s_qt & 1) * (Q_BYTES >> 4));
+            const uint64_t kdesc = desc_k0 + static_cast<uint64_t>(s_j * (KV_TILE_BYTES >> 4));
+            const uint32_t idesc = s_j == nkv - 1 ? idesc_s_tail : idesc_s_full;
+            const uint32_t ts = tmem_base + (s_i & 1) * BKV;
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < DH / 16; ++k)
-                    umma_bf16_ss(tmem_base + (i & 1) * BKV, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
-                umma_commit(&s_full[i & 1]);
-                if (j == nkv - 1) umma_commit(&q_empty[qt & 1]);
-            };
-            issue_s(0);
-            if (nsteps > 1) issue_s(1);
-            for (int i = 0; i < nsteps; ++i) {
-                const int qt = i / nkv, j = i - qt * nkv;
+                    umma_bf16_ss(ts, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+                umma_commit(&s_full[s_i & 1]);
+                if (s_j == nkv - 1) umma_commit(&q_empty[s_qt & 1]);
+            }
+            __syncwarp();
+            ++s_i;
+            if (++s_j == nkv) { s_j = 0; ++s_qt; }
+        };
+        issue_s();
+        if (nsteps > 1) issue_s();
+        int i = 0;
+        for (int qt = 0; qt < nq; ++qt) {
+            for (int j = 0; j < nkv; ++j, ++i) {
                 if (qt == 0) mbar_wait(&v_full[j], 0);
                 mbar_wait(&p_full[i & 1], (i >> 1) & 1);
                 if (j == 0 && qt > 0) mbar_wait(o_free, (qt - 1) & 1);
                 tcgen05_fence_after();
                 // V tile [kv rows][64 d] is an MN-major B operand: 128-byte rows along N = d,
                 // 8-row (k) groups 1024 B apart; one UMMA K-step (16 kv rows) = 2048 B.
-                const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + j * KV_TILE_BYTES), 16, 1024);
+                const uint64_t vdesc = desc_v0 + static_cast<uint64_t>(j * (KV_TILE_BYTES >> 4));
                 const uint32_t tp = tmem_base + (i & 1) * BKV;          // P: bf16 pairs, 8 columns per K-step
-                const int ksteps = (j == nkv - 1 ? p.tail_cols : BKV) / 16;
-                for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t acc = (j | k) != 0 ? 1u : 0u;
-                    umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, acc);
-                    umma_bf16_ts(tmem_l, tp + 8 * k, onesdesc, idesc_l, acc);
+                const bool last = j == nkv - 1;
+                if (elect_one()) {
+                    if (!last) {
+#pragma unroll
+                        for (int k = 0; k < BKV / 16; ++k)
+                            umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+                    } else {
+                        const int ksteps = p.tail_cols >> 4;
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(pv_done);
+                    if (last) umma_commit(o_full);
                 }
-                umma_commit(pv_done);
-                if (j == nkv - 1) umma_commit(o_full);
-                if (i + 2 < nsteps) issue_s(i + 2);       // overwrites P_i's buffer: ordered after PV_i
+                __syncwarp();
+                if (s_i < nsteps) issue_s();              // overwrites P_i's buffer: ordered after PV_i
             }
         }
     } else {
@@ -199,11 +210,11 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         const float thresh = RESCALE_LOG2 / sc;
 
         // out[row] = O / l for query tile qt (after its last PV has retired), then free O
-        auto epilogue = [&](int qt) {
+        auto epilogue = [&](int qt, float l) {
             mbar_wait(o_full, qt & 1);
             tcgen05_fence_after();
             if (qt * BQ + warp * 32 < p.T) {
-                const float inv = 1.0f / __uint_as_float(tmem_ld_32x32b_x1(tmem_base + lane_addr + COL_L));
+                const float inv = 1.0f / l;
                 const int t = qt * BQ + r;
                 uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<long long>(row0 + t) * D + h * DH);
 #pragma unroll
@@ -227,11 +238,16 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         };
 
         float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
+        float l_run = 0.f, l_prev = 0.f;      // running row sum (relative to m_run); previous tile's final sum
         for (int qt = 0; qt < nq; ++qt) {
             const bool active = qt * BQ + warp * 32 < p.T;           // warp-uniform
             for (int j = 0; j < nkv; ++j) {
                 const int i = qt * nkv + j;
                 const uint32_t t_s = tmem_base + lane_addr + (i & 1) * BKV;
+                if (j == 0) {                 // new query tile: keep the finished tile's row sum for its epilogue
+                    l_prev = l_run;
+                    l_run = 0.f;
+                }
                 mbar_wait(&s_full[i & 1], (i >> 1) & 1);
                 tcgen05_fence_after();
                 if (active) {
@@ -269,8 +285,9 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                             const float f = fast_exp2((m_run - m_new) * sc);
                             mbar_wait(pv_done, (i - 1) & 1);
                             tcgen05_fence_after();
+                            l_run *= f;
 #pragma unroll 1
-                            for (int c = 0; c < 5; ++c) {            // O: 4 chunks, l: 1 chunk (contiguous)
+                            for (int c = 0; c < 4; ++c) {
                                 uint32_t o[16];
                                 tmem_ld_32x32b_x16(t_o + c * 16, o);
                                 tmem_ld_wait();
@@ -283,24 +300,30 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                         }
                     }
                     const float nm = -m_run * sc;
+                    float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                         if (c < nch) {
                             uint32_t pk[8];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                pk[e] = pack_bf16x2(fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e]), sc, nm)),
-                                                    fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e + 1]), sc, nm)));
+                            for (int e = 0; e < 8; ++e) {
+                                const float p0 = fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e]), sc, nm));
+                                const float p1 = fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e + 1]), sc, nm));
+                                rs0 += p0;
+                                rs1 += p1;
+                                pk[e] = pack_bf16x2(p0, p1);
+                            }
                             tmem_st_32x32b_x8(t_s + c * 8, pk);      // P over the S buffer: 2 bf16 per column
                         }
+                    l_run += rs0 + rs1;
                     tmem_st_wait();
                 }
                 tcgen05_fence_before();
                 mbar_arrive(&p_full[i & 1]);
-                if (j == 0 && qt > 0) epilogue(qt - 1);    // deferred: overlaps PV of the previous tile
+                if (j == 0 && qt > 0) epilogue(qt - 1, l_prev);   // deferred: overlaps this tile's first MMAs
             }
         }
-        epilogue(nq - 1);
+        epilogue(nq - 1, l_run);
     }
 
     tcgen05_fence_before();

@@ -52,7 +52,6 @@ struct esmdiff_ctx {
     int num_sms = 148;
     std::string err;
     int64_t launches = 0;
-    int gemm_bn = 0;           // 0 = choose per shape, 192 / 256 = force (ESMDIFF_GEMM_BN; tuning only)
     int attn_variant = 0;      // 0 = resident K/V where it fits, 1 = always the streaming kernel (ESMDIFF_ATTN=stream)
     EncodeTiledFn encode = nullptr;
 
@@ -171,17 +170,9 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     if (K % gemm::BK != 0 || K <= 0) return c->fail("gemm: K must be a positive multiple of 64");
     const int max_clusters = c->num_sms / 2;
     const int m_tiles = (M + gemm::BM - 1) / gemm::BM;
-    // tile width: 256, or 192 for the residual epilogue when that wastes less of the last wave
-    int BN = 256;
-    if (epi == gemm::EPI_RESID_F32 && N % 192 == 0 && c->gemm_bn != 256) {
-        auto cost = [&](int bn) {
-            const int64_t tiles = (int64_t)m_tiles * ((N + bn - 1) / bn);
-            return (tiles + max_clusters - 1) / max_clusters * bn;
-        };
-        if (c->gemm_bn == 192 || N % 256 != 0 || cost(192) < cost(256)) BN = 192;
-    }
+    const int BN = 256;
     if ((epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_RESID_F32) && N % BN != 0)
-        return c->fail("gemm: SwiGLU / residual epilogues need N % 256 == 0 (residual: or N % 192 == 0)");
+        return c->fail("gemm: SwiGLU / residual epilogues need N % 256 == 0");
     CUtensorMap ta, tb, tc;
     if (get_tmap(c, A, M, K, K, gemm::BM_CTA, &ta)) return 1;
     if (get_tmap(c, W, N, K, K, BN / 2, &tb)) return 1;
@@ -192,9 +183,8 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
             return c->fail("gemm: bf16 output needs a 16-byte aligned base and row stride");
         if (get_tmap(c, out, M, out_cols, ldo, 32, &tc)) return 1;
     } else if (epi == gemm::EPI_RESID_F32) {
-        if (ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15))
-            return c->fail("gemm: fp32 residual needs a 16-byte aligned base and row stride");
-        if (get_tmap(c, out, M, N, ldo, 32, &tc, true)) return 1;
+        if (ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31))
+            return c->fail("gemm: fp32 residual needs a 32-byte aligned base and row stride");
     }
     gemm::Params p;
     p.M = M; p.N = N; p.K = K;
@@ -217,10 +207,7 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     }
     switch (epi) {
         case gemm::EPI_STORE_BF16: LAUNCH_GEMM(gemm::EPI_STORE_BF16, 256) break;
-        case gemm::EPI_RESID_F32:
-            if (BN == 192) LAUNCH_GEMM(gemm::EPI_RESID_F32, 192)
-            else LAUNCH_GEMM(gemm::EPI_RESID_F32, 256)
-            break;
+        case gemm::EPI_RESID_F32: LAUNCH_GEMM(gemm::EPI_RESID_F32, 256) break;
         case gemm::EPI_SWIGLU_BF16: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16, 256) break;
         case gemm::EPI_BIAS_GELU_F32: LAUNCH_GEMM(gemm::EPI_BIAS_GELU_F32, 256) break;
         case gemm::EPI_BIAS_F32: LAUNCH_GEMM(gemm::EPI_BIAS_F32, 256) break;
@@ -571,7 +558,6 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->layers.resize(cfg->n_layers);
-    if (const char* e = getenv("ESMDIFF_GEMM_BN")) c->gemm_bn = atoi(e);
     if (const char* e = getenv("ESMDIFF_ATTN")) c->attn_variant = strcmp(e, "stream") == 0 ? 1 : 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

@@ -47,11 +47,11 @@ enum Epilogue {
 // one pipeline stage.
 template <int EPI, int BN> struct Cfg {
     static_assert(BN == 256 || BN == 192, "tile widths instantiated");
-    static_assert(BN == 256 || EPI == EPI_RESID_F32, "BN = 192 only with the 32-column residual epilogue");
+    static_assert(BN == 256, "BN = 192 compiles for the 32-column epilogues only; not instantiated");
     static constexpr int BN_CTA = BN / 2;                 // W rows each CTA loads
     static constexpr int B_BYTES = BN_CTA * BK * 2;       // 16 / 12 KiB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BOXES = EPI == EPI_RESID_F32 ? 2 : 1;
+    static constexpr int BOXES = EPI == EPI_RESID_F32 ? 0 : 1;    // the residual epilogue stages nothing
     static constexpr int STG_BYTES = EPI_WARPS * BOXES * BOX_BYTES;
     static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STG_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT < MAX_STAGES ? STAGES_FIT : MAX_STAGES;
@@ -74,6 +74,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // SwiGLU gate for a bf16 result: ex2/rcp approximations (2 ulp of fp32) are far below the bf16
 // rounding of the output (2^-9)
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// One 128-byte line (32 fp32) of a residual-stream row <-> registers, as four 256-bit accesses.
+__device__ __forceinline__ void ld_row128(float* r, const float* g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(r[8 * i]), "=f"(r[8 * i + 1]), "=f"(r[8 * i + 2]), "=f"(r[8 * i + 3]),
+                       "=f"(r[8 * i + 4]), "=f"(r[8 * i + 5]), "=f"(r[8 * i + 6]), "=f"(r[8 * i + 7])
+                     : "l"(g + 8 * i)
+                     : "memory");
+}
+__device__ __forceinline__ void st_row128(float* g, const float* r) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("st.global.v8.f32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+                     ::"f"(r[8 * i]), "f"(r[8 * i + 1]), "f"(r[8 * i + 2]), "f"(r[8 * i + 3]),
+                       "f"(r[8 * i + 4]), "f"(r[8 * i + 5]), "f"(r[8 * i + 6]), "f"(r[8 * i + 7]), "l"(g + 8 * i)
+                     : "memory");
+}
 
 // One 16-byte chunk of a 128-byte staging row under the 128B swizzle TMA expects.
 __device__ __forceinline__ void st_swz16(uint8_t* box, int row, int chunk, uint32_t a, uint32_t b, uint32_t c,
@@ -101,8 +120,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
     uint64_t* empty = bars + MAX_STAGES;   // [STAGES]  MMA -> TMA, multicast to both CTAs
     uint64_t* tfull = bars + 2 * MAX_STAGES;   // [2]   MMA -> epilogue, multicast to both CTAs
     uint64_t* tempty = tfull + 2;          // [2]       epilogue warps of both CTAs -> MMA (leader's copy)
-    uint64_t* xfull = tempty + 2;          // [EPI_WARPS][2]  residual epilogue: x box landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xfull + 2 * EPI_WARPS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,7 +144,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], 2 * EPI_WARPS);
         }
-        for (int a = 0; a < 2 * EPI_WARPS; ++a) mbar_init(&xfull[a], 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -158,9 +175,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread of the leader CTA) =====================
-        if (rank == 0 && lane == 0) {
+        // ===================== MMA issuer (leader CTA) =====================
+        // The whole warp walks the schedule so that control flow, stage counters and descriptors
+        // are warp-uniform (uniform registers, no per-MMA re-broadcast); one elected lane issues
+        // the tcgen05 instructions.  The next stage's barrier is probed before this stage's MMAs
+        // are issued, so its ~90-cycle try_wait latency is off the issue path.
+        if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0);
+            const uint64_t desc0 = umma_desc_sw128(smem_u32(smem), 16, 1024);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -169,22 +191,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                bool ready = mbar_try_wait(&full[stage], phase);
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    if (!ready) mbar_wait(&full[stage], phase);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-                    const uint64_t bdesc = umma_desc_sw128(sa + A_BYTES, 16, 1024);
+                    const int next = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t next_phase = next == 0 ? phase ^ 1 : phase;
+                    ready = kb + 1 < kblocks ? mbar_try_wait(&full[next], next_phase) : false;
+                    const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * (STAGE_BYTES >> 4));
+                    const uint64_t bdesc = adesc + (A_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // +32 bytes (16 bf16) along K inside the 128B swizzle row = +2 encoded
-                        umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc,
-                                          (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 bytes (16 bf16) along K inside the 128B swizzle row = +2 encoded
+                            umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        umma_commit_pair(&empty[stage]);  // frees the slot in both CTAs when the MMAs retire
                     }
-                    umma_commit_pair(&empty[stage]);  // frees the slot in both CTAs when the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    __syncwarp();
+                    stage = next;
+                    phase = next_phase;
                 }
-                umma_commit_pair(&tfull[acc]);        // accumulators ready in both CTAs
+                if (elect_one()) umma_commit_pair(&tfull[acc]);   // accumulators ready in both CTAs
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -195,7 +224,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         uint8_t* box = stg_all + (warp - 4) * BOXES * BOX_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t xg = 0;                              // residual epilogue: running x-box counter
+        float xres[EPI == EPI_RESID_F32 ? 64 : 1];    // residual epilogue: two 32-float register sets of x
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int nb = tile % p.n_tiles;
             const int n0 = nb * BN + half * (BN / 2);
@@ -263,56 +292,47 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     bulk_commit_group();
                 }
             } else if constexpr (EPI == EPI_RESID_F32) {
-                // residual stream update x = x + acc / scale.  The old x tile comes in through TMA
-                // one 32x32 box ahead (issued before the accumulator is ready), is updated in
-                // shared memory (thread = row, swizzled 16-byte chunks: conflict-free) and leaves
-                // as a TMA tile store: the epilogue issues no global loads or stores of its own.
-                // (Measured alternatives on B200, out_proj / W2 shapes at M = 16254: TMA reduce-add
-                // 680 / 1152 TFLOP/s, per-row register prefetch 461 / 1056, transposed coalesced
-                // RMW 535 / 1080, this form 822 / 1168.)
+                // residual stream update x = x + acc / scale, entirely in registers: thread = row,
+                // one 32-column chunk of a row is one 128-byte line, moved as four 256-bit
+                // loads/stores.  Nothing touches shared memory here, which matters because the main
+                // loop already runs at the shared-memory bandwidth limit (TMA fill + UMMA operand
+                // reads ~ 125 B/clk/SM): the earlier TMA-staged form (load box -> add in smem ->
+                // store box, 512 KiB of extra smem traffic per tile) held out_proj to 0.74-0.93
+                // PFLOP/s.  Loads run two chunks ahead in two register sets; the first two chunks of
+                // the NEXT tile are requested while this tile drains, so they land during its main
+                // loop.  acc / scale is evaluated as acc * (1 / scale): <= 1 ulp(fp32) from the
+                // reference's division, far below the bf16 rounding of the GEMM operands.
                 constexpr int NCH = (BN / 2) / 32;
-                uint64_t* xbar = xfull + (warp - 4) * 2;
-                auto issue_x_load = [&](uint32_t g, int col, int row) {     // lane 0 only
-                    bulk_wait_group_read<0>();           // the store that last used this box has read it
-                    mbar_arrive_expect_tx(&xbar[g & 1], BOX_BYTES);
-                    tma_load_2d(box + (g & 1) * BOX_BYTES, &tmC, &xbar[g & 1], col, row);
+                static_assert(NCH == 4, "two alternating register sets need an even chunk count");
+                float* xg = reinterpret_cast<float*>(p.out);
+                const float inv = 1.0f / p.scale;
+                auto chunk_ptr = [&](int t, int c) {
+                    const long long row = static_cast<long long>(t / p.n_tiles) * BM + rank * BM_CTA + q * 32 + lane;
+                    return xg + row * p.ldo + (t % p.n_tiles) * BN + half * (BN / 2) + c * 32;
                 };
-                if (tile == cluster_id && lane == 0) issue_x_load(xg, n0, row_base);
-#pragma unroll 1
-                for (int c = 0; c < NCH; ++c, ++xg) {
-                    if (lane == 0) {                     // prefetch the next box (this or the next tile)
-                        if (c + 1 < NCH) {
-                            issue_x_load(xg + 1, n0 + (c + 1) * 32, row_base);
-                        } else if (tile + num_clusters < num_tiles) {
-                            const int nt = tile + num_clusters;
-                            issue_x_load(xg + 1, (nt % p.n_tiles) * BN + half * (BN / 2),
-                                         (nt / p.n_tiles) * BM + rank * BM_CTA + q * 32);
-                        }
-                    }
-                    if (c == 0) {
-                        mbar_wait(&tfull[acc], acc_phase);
-                        tcgen05_fence_after();
-                    }
+                auto row_ok = [&](int t) { return (t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA + q * 32 + lane < p.M; };
+                const bool ok = row_ok(tile);
+                if (tile == cluster_id && ok) {         // first tile of this CTA pair: nothing prefetched yet
+                    ld_row128(xres, chunk_ptr(tile, 0));
+                    ld_row128(xres + 32, chunk_ptr(tile, 1));
+                }
+                const int nt = tile + num_clusters;
+                const bool ok_next = nt < num_tiles && row_ok(nt);
+                mbar_wait(&tfull[acc], acc_phase);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    float* xr = (c & 1) ? xres + 32 : xres;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
-                    mbar_wait(&xbar[xg & 1], (xg >> 1) & 1);
                     tmem_ld_wait();
-                    uint8_t* bx = box + (xg & 1) * BOX_BYTES + lane * 128;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4* ptr = reinterpret_cast<float4*>(bx + ((j ^ (lane & 7)) << 4));
-                        float4 y = *ptr;
-                        y.x += __uint_as_float(v[4 * j]) / p.scale;
-                        y.y += __uint_as_float(v[4 * j + 1]) / p.scale;
-                        y.z += __uint_as_float(v[4 * j + 2]) / p.scale;
-                        y.w += __uint_as_float(v[4 * j + 3]) / p.scale;
-                        *ptr = y;
-                    }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, box + (xg & 1) * BOX_BYTES, n0 + c * 32, row_base);
-                        bulk_commit_group();
+                    for (int j = 0; j < 32; ++j) xr[j] = fmaf(__uint_as_float(v[j]), inv, xr[j]);
+                    if (ok) st_row128(chunk_ptr(tile, c), xr);
+                    if (c + 2 < NCH) {
+                        if (ok) ld_row128(xr, chunk_ptr(tile, c + 2));
+                    } else if (ok_next) {
+                        ld_row128(xr, chunk_ptr(nt, c + 2 - NCH));
                     }
                 }
             } else {

@@ -173,6 +173,19 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         : "memory");
 }
 
+// One lane of a converged warp (the same lane for the whole kernel in practice).  Wrapping only the
+// tcgen05 / TMA issue in `if (elect_one())` keeps the surrounding role loop warp-uniform, so
+// descriptors and loop counters stay in uniform registers instead of being re-broadcast per MMA.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05: TMEM management ----------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

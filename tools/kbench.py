@@ -43,7 +43,7 @@ def engine(**env):
 
 def bench_gemm(flush):
     g = torch.Generator(device="cuda").manual_seed(4)
-    engs = {"auto": engine(), "bn256": engine(ESMDIFF_GEMM_BN="256"), "bn192": engine(ESMDIFF_GEMM_BN="192")}
+    engs = {"auto": engine()}
     for M in (16254, 9546, 25800):
         for (N, K, epi, name) in [(4608, 1536, 0, "qkv"), (1536, 1536, 1, "out_proj"), (8192, 1536, 2, "w1_swiglu"),
                                   (1536, 4096, 1, "w2")]:
