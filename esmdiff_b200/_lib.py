@@ -91,6 +91,9 @@ _SIGS = {
                                        C.POINTER(C.c_int64)]),
     "esmdiff_op_gemm": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64,
                                   _P, C.c_float, _P]),
+    "esmdiff_op_gemm_ln": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64,
+                                     _P, C.c_float, _P, _P, _P, _P, _P]),
+    "esmdiff_op_fold_layernorm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "esmdiff_op_layernorm": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "esmdiff_op_qk_norm_rope": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "esmdiff_op_attention": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),

@@ -185,7 +185,8 @@ embed_kernel(const long long* __restrict__ seq, const long long* __restrict__ xt
              const float* __restrict__ seq_embed, const float* __restrict__ struct_embed,
              const float* __restrict__ const_vec, const float* __restrict__ aux,
              long long aux_row_stride, float* __restrict__ x, int M, int D, int seq_vocab,
-             int struct_vocab, int* __restrict__ err) {
+             int struct_vocab, int* __restrict__ err, __nv_bfloat16* __restrict__ xb,
+             float2* __restrict__ stats) {
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -209,6 +210,16 @@ embed_kernel(const long long* __restrict__ seq, const long long* __restrict__ xt
         r.z = (va.z + vc.z) + vb.z; r.w = (va.w + vc.w) + vb.w;
         if (d) { const float4 vd = d[i]; r.x += vd.x; r.y += vd.y; r.z += vd.z; r.w += vd.w; }
         o[i] = r;
+        if (xb != nullptr) {
+            // LayerNorm folded through the first QKV GEMM (gemm.cuh): bf16 copy of the row and the
+            // (mean, M2) of each 128-column span (= one trip of this loop across the warp)
+            reinterpret_cast<uint2*>(xb + static_cast<long long>(row) * D)[i] =
+                make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+            const float mean = warp_sum((r.x + r.y) + (r.z + r.w)) * (1.0f / 128.0f);
+            const float a0 = r.x - mean, a1 = r.y - mean, a2 = r.z - mean, a3 = r.w - mean;
+            const float m2 = warp_sum((a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3));
+            if (lane == 0) stats[static_cast<long long>(row) * (D / 128) + i / 32] = make_float2(mean, m2);
+        }
     }
 }
 
@@ -266,6 +277,40 @@ time_embed_out_kernel(const float* __restrict__ hidden, const float* __restrict_
     for (int k = lane; k < D; k += 32) s += w2[static_cast<long long>(j) * D + k] * hidden[k];
     s = warp_sum(s);
     if (lane == 0) cond[j] = s + b2[j];
+}
+
+// LayerNorm folded into the following Linear (gemm.cuh, *_LN epilogues), one warp per output row n:
+//   dst[n, k]  = bf16(W[src(n), k] * gamma[k])
+//   colsum[n]  = sum_k float(dst[n, k])          (of the ROUNDED weights: it multiplies the row mean)
+//   bias[n]    = sum_k beta[k] * W[src(n), k]    (fp32; beta may be null)
+// src(n) applies the SwiGLU gate/up interleave of convert_rows_bf16_kernel when swiglu_hidden > 0.
+__global__ void __launch_bounds__(256)
+fold_layernorm_weight_kernel(const float* __restrict__ src, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ dst,
+                             float* __restrict__ colsum, float* __restrict__ bias, long long rows,
+                             long long cols, int swiglu_hidden) {
+    const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    long long sr = r;
+    if (swiglu_hidden > 0) {
+        const long long blk = r / 256, within = r % 256;
+        sr = within < 128 ? blk * 128 + within : swiglu_hidden + blk * 128 + (within - 128);
+    }
+    float cs = 0.f, bs = 0.f;
+    for (long long k = lane; k < cols; k += 32) {
+        const float w = src[sr * cols + k];
+        const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k]);
+        dst[r * cols + k] = wf;
+        cs += __bfloat162float(wf);
+        if (beta != nullptr) bs += beta[k] * w;
+    }
+    cs = warp_sum(cs);
+    bs = warp_sum(bs);
+    if (lane == 0) {
+        colsum[r] = cs;
+        bias[r] = bs;
+    }
 }
 
 // fp32 -> bf16 weight conversion with an optional row permutation (SwiGLU gate/up interleave).

@@ -39,6 +39,11 @@ struct LayerW {
     float *ln1_w = nullptr, *ln1_b = nullptr, *qln_w = nullptr, *kln_w = nullptr;
     float *ln2_w = nullptr, *ln2_b = nullptr;
     bf16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+    // LayerNorm folded through the QKV / W1 GEMMs (gemm.cuh): fp32 masters kept from set_weight
+    // until finalize folds gamma into the bf16 weights; c = colsum(gamma.W), b = beta W^T
+    float *wqkv_f32 = nullptr, *w1_f32 = nullptr;
+    float *cqkv = nullptr, *bqkv = nullptr, *c1 = nullptr, *b1 = nullptr;
+    bool dirty = true;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -53,6 +58,7 @@ struct esmdiff_ctx {
     std::string err;
     int64_t launches = 0;
     int attn_variant = 0;      // 0 = resident K/V where it fits, 1 = always the streaming kernel (ESMDIFF_ATTN=stream)
+    bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
     EncodeTiledFn encode = nullptr;
 
     std::vector<LayerW> layers;
@@ -68,6 +74,7 @@ struct esmdiff_ctx {
     // workspace (grows with the largest B*T seen)
     int64_t ws_rows = 0;
     float *x = nullptr, *headh = nullptr, *logits_ws = nullptr;
+    float2* stats = nullptr;                           // [rows][d_model / 128] partial (mean, M2) of x
     bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;
     float *cond = nullptr, *te_hidden = nullptr, *inv_freq = nullptr;
     float *cos_t = nullptr, *sin_t = nullptr;
@@ -165,24 +172,43 @@ static int get_tmap(esmdiff_ctx* c, const void* base, uint64_t rows, uint64_t co
 // ------------------------------------------------------------------------------------------------
 // kernel launchers
 // ------------------------------------------------------------------------------------------------
+struct GemmLN {                // operands of the LayerNorm-folded epilogues (gemm.cuh)
+    const float2* stats_in = nullptr;
+    const float* colsum = nullptr;
+    float2* stats_out = nullptr;
+    bf16* xb_out = nullptr;
+};
+
 static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, int M, int N, int K,
-                       void* out, int64_t ldo, const float* bias, float scale, cudaStream_t st) {
+                       void* out, int64_t ldo, const float* bias, float scale, cudaStream_t st,
+                       const GemmLN& ln = GemmLN()) {
     if (K % gemm::BK != 0 || K <= 0) return c->fail("gemm: K must be a positive multiple of 64");
     const int max_clusters = c->num_sms / 2;
     const int m_tiles = (M + gemm::BM - 1) / gemm::BM;
     const int BN = 256;
-    if ((epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_RESID_F32) && N % BN != 0)
-        return c->fail("gemm: SwiGLU / residual epilogues need N % 256 == 0");
+    const bool is_store = epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_STORE_BF16_LN;
+    const bool is_swiglu = epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_SWIGLU_BF16_LN;
+    const bool is_resid = epi == gemm::EPI_RESID_F32 || epi == gemm::EPI_RESID_F32_LN;
+    if ((is_swiglu || is_resid || epi == gemm::EPI_STORE_BF16_LN) && N % BN != 0)
+        return c->fail("gemm: SwiGLU / residual / LayerNorm-folded epilogues need N % 256 == 0");
+    if (epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_SWIGLU_BF16_LN) {
+        if (!ln.stats_in || !ln.colsum || !bias || K % 256 != 0 || K > 1536)
+            return c->fail("gemm: LayerNorm-folded epilogue needs statistics, colsum, bias and K % 256 == 0 <= 1536");
+    }
+    if (epi == gemm::EPI_RESID_F32_LN) {
+        if (!ln.stats_out || !ln.xb_out || ldo != N)
+            return c->fail("gemm: residual+statistics epilogue needs stats_out, xb_out and a dense [M, N] stream");
+    }
     CUtensorMap ta, tb, tc;
     if (get_tmap(c, A, M, K, K, gemm::BM_CTA, &ta)) return 1;
     if (get_tmap(c, W, N, K, K, BN / 2, &tb)) return 1;
     tc = ta;                                     // unused by the direct-store epilogues
-    if (epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_SWIGLU_BF16) {
-        const int out_cols = epi == gemm::EPI_SWIGLU_BF16 ? N / 2 : N;
+    if (is_store || is_swiglu) {
+        const int out_cols = is_swiglu ? N / 2 : N;
         if (ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 15))
             return c->fail("gemm: bf16 output needs a 16-byte aligned base and row stride");
         if (get_tmap(c, out, M, out_cols, ldo, 32, &tc)) return 1;
-    } else if (epi == gemm::EPI_RESID_F32) {
+    } else if (is_resid) {
         if (ldo % 8 != 0 || (reinterpret_cast<uintptr_t>(out) & 31))
             return c->fail("gemm: fp32 residual needs a 32-byte aligned base and row stride");
     }
@@ -191,9 +217,15 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     p.m_tiles = m_tiles;
     p.n_tiles = (N + BN - 1) / BN;
     p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
+    p.stats_in = ln.stats_in; p.colsum = ln.colsum; p.stats_out = ln.stats_out; p.xb_out = ln.xb_out;
+    p.ln_eps = 1e-5f;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
-    ProfScope prof(c, epi, 2.0 * M * (double)N * K, st);
+    // profile kinds: the LayerNorm-folded variants are booked under their plain counterparts
+    const int kind = epi == gemm::EPI_STORE_BF16_LN ? gemm::EPI_STORE_BF16
+                   : epi == gemm::EPI_RESID_F32_LN ? gemm::EPI_RESID_F32
+                   : epi == gemm::EPI_SWIGLU_BF16_LN ? gemm::EPI_SWIGLU_BF16 : epi;
+    ProfScope prof(c, kind, 2.0 * M * (double)N * K, st);
 #define LAUNCH_GEMM(E, BNV)                                                                    \
     {                                                                                          \
         static bool attr_set = false;                                                          \
@@ -211,6 +243,9 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
         case gemm::EPI_SWIGLU_BF16: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16, 256) break;
         case gemm::EPI_BIAS_GELU_F32: LAUNCH_GEMM(gemm::EPI_BIAS_GELU_F32, 256) break;
         case gemm::EPI_BIAS_F32: LAUNCH_GEMM(gemm::EPI_BIAS_F32, 256) break;
+        case gemm::EPI_STORE_BF16_LN: LAUNCH_GEMM(gemm::EPI_STORE_BF16_LN, 256) break;
+        case gemm::EPI_RESID_F32_LN: LAUNCH_GEMM(gemm::EPI_RESID_F32_LN, 256) break;
+        case gemm::EPI_SWIGLU_BF16_LN: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16_LN, 256) break;
         default: return c->fail("gemm: unknown epilogue");
     }
 #undef LAUNCH_GEMM
@@ -335,7 +370,7 @@ static int launch_time_embed(esmdiff_ctx* c, float sigma, float* cond, cudaStrea
 static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     if (M <= c->ws_rows) return 0;
     // free the previous workspace buffers
-    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf};
+    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf, c->stats};
     for (void* o : olds)
         if (o) {
             cudaFree(o);
@@ -345,7 +380,8 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     c->tmaps.clear();
     const int64_t D = c->cfg.d_model, F = c->cfg.ffn_hidden, V = c->cfg.n_structure_heads;
     c->x = nullptr; c->headh = nullptr; c->logits_ws = nullptr;
-    c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr;
+    c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr; c->stats = nullptr;
+    if (c->alloc(&c->stats, M * (D / 128))) return 1;
     if (c->alloc(&c->x, M * D)) return 1;
     if (c->alloc(&c->headh, M * D)) return 1;
     if (c->alloc(&c->logits_ws, M * V)) return 1;
@@ -378,13 +414,35 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
     ew::embed_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const long long*>(seq),
                                             reinterpret_cast<const long long*>(xt), c->seq_embed,
                                             c->struct_embed, c->const_vec, aux, aux_stride, c->x, M, D,
-                                            c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err);
+                                            c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err,
+                                            c->ln_fold ? c->xn : nullptr, c->stats);
     }
     c->launches++;
     CK(cudaGetLastError());
 
     for (int l = 0; l < c->cfg.n_layers; ++l) {
         const LayerW& w = c->layers[l];
+        if (c->ln_fold) {
+            // pre-LayerNorms folded through the GEMMs: xn is the bf16 copy of the RAW stream and
+            // stats its per-row partial statistics, both written by the producer of x (embedding
+            // kernel / residual epilogue); gamma is folded into wqkv / w1 at finalize
+            GemmLN use, make;
+            use.stats_in = c->stats;
+            make.stats_out = c->stats;
+            make.xb_out = c->xn;
+            const bool last = l == c->cfg.n_layers - 1;           // the final norm + head use the LN kernel
+            use.colsum = w.cqkv;
+            if (launch_gemm(c, gemm::EPI_STORE_BF16_LN, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, w.bqkv, 1.f, st, use)) return 1;
+            if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
+            if (launch_attention(c, c->qkv, c->att, B, T, H, st)) return 1;
+            if (launch_gemm(c, gemm::EPI_RESID_F32_LN, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st, make)) return 1;
+            // block 0's geometric attention contributes exactly 0 on this path
+            use.colsum = w.c1;
+            if (launch_gemm(c, gemm::EPI_SWIGLU_BF16_LN, c->xn, w.w1, M, 2 * F, D, c->hbuf, F, w.b1, 1.f, st, use)) return 1;
+            if (launch_gemm(c, last ? gemm::EPI_RESID_F32 : gemm::EPI_RESID_F32_LN, c->hbuf, w.w2, M, D, F, c->x, D,
+                            nullptr, rs, st, make)) return 1;
+            continue;
+        }
         if (launch_layernorm(c, c->x, w.ln1_w, w.ln1_b, c->xn, M, D, st)) return 1;
         if (launch_gemm(c, gemm::EPI_STORE_BF16, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, nullptr, 1.f, st)) return 1;
         if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
@@ -434,6 +492,8 @@ struct Slot {
     Kind kind;
     void** dst;
     std::vector<int64_t> shape;
+    float** master = nullptr;      // LayerNorm-folded Linears: the fp32 copy is kept until finalize
+    int layer = -1;                // block whose folded weights this key invalidates
 };
 }  // namespace
 
@@ -481,15 +541,25 @@ static bool resolve_key(esmdiff_ctx* c, const std::string& key, Slot* s) {
         LayerW& w = c->layers[l];
         const std::string r = k.substr(dot + 1);
         if (r.rfind("geom_attn.", 0) == 0) return skip();      // exact zero on this path (A6)
-        if (r == "attn.layernorm_qkv.0.weight") return f32(&w.ln1_w, {D});
-        if (r == "attn.layernorm_qkv.0.bias") return f32(&w.ln1_b, {D});
-        if (r == "attn.layernorm_qkv.1.weight") return b16(&w.wqkv, {3 * D, D});
+        if (r == "attn.layernorm_qkv.0.weight") { f32(&w.ln1_w, {D}); s->layer = l; return true; }
+        if (r == "attn.layernorm_qkv.0.bias") { f32(&w.ln1_b, {D}); s->layer = l; return true; }
+        if (r == "attn.layernorm_qkv.1.weight") {
+            b16(&w.wqkv, {3 * D, D});
+            s->layer = l;
+            if (c->ln_fold) s->master = &w.wqkv_f32;
+            return true;
+        }
         if (r == "attn.q_ln.weight") return f32(&w.qln_w, {D});
         if (r == "attn.k_ln.weight") return f32(&w.kln_w, {D});
         if (r == "attn.out_proj.weight") return b16(&w.wo, {D, D});
-        if (r == "ffn.0.weight") return f32(&w.ln2_w, {D});
-        if (r == "ffn.0.bias") return f32(&w.ln2_b, {D});
-        if (r == "ffn.1.weight") { *s = {K_BF16_SWIGLU, (void**)&w.w1, {2 * F, D}}; return true; }
+        if (r == "ffn.0.weight") { f32(&w.ln2_w, {D}); s->layer = l; return true; }
+        if (r == "ffn.0.bias") { f32(&w.ln2_b, {D}); s->layer = l; return true; }
+        if (r == "ffn.1.weight") {
+            *s = {K_BF16_SWIGLU, (void**)&w.w1, {2 * F, D}};
+            s->layer = l;
+            if (c->ln_fold) s->master = &w.w1_f32;
+            return true;
+        }
         if (r == "ffn.3.weight") return b16(&w.w2, {D, F});
         return false;
     }
@@ -559,6 +629,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->layers.resize(cfg->n_layers);
     if (const char* e = getenv("ESMDIFF_ATTN")) c->attn_variant = strcmp(e, "stream") == 0 ? 1 : 0;
+    if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -587,6 +658,10 @@ int esmdiff_destroy(esmdiff_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->owned)
         if (p) cudaFree(p);
+    for (LayerW& w : c->layers) {
+        if (w.wqkv_f32) cudaFree(w.wqkv_f32);
+        if (w.w1_f32) cudaFree(w.w1_f32);
+    }
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     delete c;
     return 0;
@@ -633,6 +708,15 @@ int esmdiff_set_weight(esmdiff_ctx* c, const char* key, const void* data, int on
         c->owned.push_back(q);
         *s.dst = q;
     }
+    if (s.layer >= 0) c->layers[s.layer].dirty = true;
+    if (s.master != nullptr) {
+        // folded at finalize (needs this block's LayerNorm weight and bias as well)
+        if (*s.master) cudaFree(*s.master);
+        *s.master = stage;
+        c->loaded.insert(key);
+        c->finalized = false;
+        return 0;
+    }
     if (s.kind == K_F32) {
         CK(cudaMemcpy(*s.dst, stage, n * sizeof(float), cudaMemcpyDeviceToDevice));
     } else {
@@ -663,6 +747,31 @@ int esmdiff_finalize_weights(esmdiff_ctx* c) {
                        (nmiss > 8 ? " ... (" + std::to_string(nmiss) + " total)" : ""));
     }
     const int D = c->cfg.d_model;
+    if (c->ln_fold) {
+        const int64_t F = c->cfg.ffn_hidden;
+        for (int l = 0; l < c->cfg.n_layers; ++l) {
+            LayerW& w = c->layers[l];
+            if (!w.dirty) continue;
+            if (!w.wqkv_f32 || !w.w1_f32)
+                return c->fail("finalize_weights: block " + std::to_string(l) + " had a LayerNorm or Linear weight "
+                               "replaced after finalize; set attn.layernorm_qkv.{0,1} and ffn.{0,1} of that block together");
+            if (!w.cqkv) {
+                if (c->alloc(&w.cqkv, 3 * D) || c->alloc(&w.bqkv, 3 * D) || c->alloc(&w.c1, 2 * F) || c->alloc(&w.b1, 2 * F))
+                    return 1;
+            }
+            ew::fold_layernorm_weight_kernel<<<(unsigned)((3 * D + 7) / 8), 256>>>(w.wqkv_f32, w.ln1_w, w.ln1_b, w.wqkv,
+                                                                                   w.cqkv, w.bqkv, 3 * D, D, 0);
+            ew::fold_layernorm_weight_kernel<<<(unsigned)((2 * F + 7) / 8), 256>>>(w.w1_f32, w.ln2_w, w.ln2_b, w.w1, w.c1,
+                                                                                   w.b1, 2 * F, D, (int)F);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            cudaFree(w.wqkv_f32);
+            cudaFree(w.w1_f32);
+            w.wqkv_f32 = nullptr;
+            w.w1_f32 = nullptr;
+            w.dirty = false;
+        }
+    }
     ew::default_tracks_kernel<<<(D + 127) / 128, 128>>>(c->plddt_w, c->plddt_b, c->res_w, c->res_b, c->ss8,
                                                         c->sasa, c->const_vec, D);
     CK(cudaGetLastError());
@@ -843,6 +952,29 @@ int esmdiff_op_gemm(esmdiff_ctx* c, int epi, const void* a, const void* w, int M
     if (!c) return 1;
     CK(cudaSetDevice(c->device));
     return launch_gemm(c, epi, (const bf16*)a, (const bf16*)w, M, N, K, out, ldo, bias, scale, (cudaStream_t)stream);
+}
+int esmdiff_op_gemm_ln(esmdiff_ctx* c, int epi, const void* a, const void* w, int M, int N, int K, void* out,
+                       int64_t ldo, const float* bias, float scale, const void* stats_in, const float* colsum,
+                       void* stats_out, void* xb_out, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    GemmLN ln;
+    ln.stats_in = (const float2*)stats_in;
+    ln.colsum = colsum;
+    ln.stats_out = (float2*)stats_out;
+    ln.xb_out = (bf16*)xb_out;
+    return launch_gemm(c, epi, (const bf16*)a, (const bf16*)w, M, N, K, out, ldo, bias, scale, (cudaStream_t)stream, ln);
+}
+int esmdiff_op_fold_layernorm(esmdiff_ctx* c, const float* w, const float* gamma, const float* beta, void* dst,
+                              float* colsum, float* bias, int64_t rows, int64_t cols, int swiglu_hidden,
+                              void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    ew::fold_layernorm_weight_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        w, gamma, beta, (bf16*)dst, colsum, bias, rows, cols, swiglu_hidden);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
 }
 int esmdiff_op_layernorm(esmdiff_ctx* c, const float* x, const float* w, const float* b, void* y, int M, int D,
                          void* stream) {

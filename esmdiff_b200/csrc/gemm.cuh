@@ -15,6 +15,16 @@
 //                                                                            interleaved per 128 offline)
 //   EPI_BIAS_GELU_F32   out = gelu(acc + bias)         coalesced st.global  (RegressionHead Linear+GELU)
 //   EPI_BIAS_F32        out = acc + bias  (ragged N = 4101, unaligned rows) (RegressionHead output)
+// LayerNorm folded through the GEMM (the pre-LN of both residual branches):
+//   LN(x) W^T = rstd * (x (gamma.W)^T - mean * colsum(gamma.W)) + beta W^T
+// so the A operand is the bf16 copy of the RAW residual stream, gamma is folded into W offline
+// (ew::fold_layernorm_weight_kernel), and the per-row mean/rstd enter in the epilogue:
+//   EPI_RESID_F32_LN    EPI_RESID_F32 + bf16 copy of the new x + per-row partial statistics
+//                       (mean, M2 over each 128-column span) for the NEXT LayerNorm
+//   EPI_STORE_BF16_LN   out = rstd * (acc - mean * c[n]) + b[n]            (QKV projection)
+//   EPI_SWIGLU_BF16_LN  the same on gate and up, then silu(gate) * up      (FFN W1)
+// This removes the stand-alone LayerNorm kernel of every block (4 B/element re-read of x and a
+// launch) at the cost of a 2 B/element extra store in the residual epilogue.
 #pragma once
 #include "ptx.cuh"
 
@@ -41,7 +51,11 @@ enum Epilogue {
     EPI_SWIGLU_BF16 = 2,
     EPI_BIAS_GELU_F32 = 3,
     EPI_BIAS_F32 = 4,
+    EPI_STORE_BF16_LN = 5,
+    EPI_RESID_F32_LN = 6,
+    EPI_SWIGLU_BF16_LN = 7,
 };
+constexpr int LN_SPAN = 128;              // columns per partial LayerNorm statistic (= epilogue warp width)
 
 // The residual epilogue double-buffers its x boxes (TMA load -> add -> TMA store), paid for with
 // one pipeline stage.
@@ -51,7 +65,7 @@ template <int EPI, int BN> struct Cfg {
     static constexpr int BN_CTA = BN / 2;                 // W rows each CTA loads
     static constexpr int B_BYTES = BN_CTA * BK * 2;       // 16 / 12 KiB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BOXES = EPI == EPI_RESID_F32 ? 0 : 1;    // the residual epilogue stages nothing
+    static constexpr int BOXES = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN) ? 0 : 1;    // the residual epilogue stages nothing
     static constexpr int STG_BYTES = EPI_WARPS * BOXES * BOX_BYTES;
     static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STG_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT < MAX_STAGES ? STAGES_FIT : MAX_STAGES;
@@ -66,6 +80,12 @@ struct Params {
     long long ldo;        // elements between output rows
     const float* bias;    // [N] or null
     float scale;          // EPI_RESID_F32: divisor of the branch output
+    // LayerNorm folded through the GEMM
+    const float2* stats_in;    // *_LN consumers: [M][K / 128] (mean, M2) partials of the A rows
+    const float* colsum;       // *_LN consumers: c[n] = sum_k bf16(gamma_k W_nk); bias = b[n] = sum_k beta_k W_nk
+    float2* stats_out;         // EPI_RESID_F32_LN: [M][N / 128] partials of the updated rows
+    __nv_bfloat16* xb_out;     // EPI_RESID_F32_LN: bf16 copy of the updated rows, [M][N]
+    float ln_eps;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -92,6 +112,53 @@ __device__ __forceinline__ void st_row128(float* g, const float* r) {
                      ::"f"(r[8 * i]), "f"(r[8 * i + 1]), "f"(r[8 * i + 2]), "f"(r[8 * i + 3]),
                        "f"(r[8 * i + 4]), "f"(r[8 * i + 5]), "f"(r[8 * i + 6]), "f"(r[8 * i + 7]), "l"(g + 8 * i)
                      : "memory");
+}
+
+// 32 bf16 of one row (64 bytes) as two 256-bit stores.
+__device__ __forceinline__ void st_row64(__nv_bfloat16* g, const uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        asm volatile("st.global.v8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+                     ::"r"(r[8 * i]), "r"(r[8 * i + 1]), "r"(r[8 * i + 2]), "r"(r[8 * i + 3]),
+                       "r"(r[8 * i + 4]), "r"(r[8 * i + 5]), "r"(r[8 * i + 6]), "r"(r[8 * i + 7]), "l"(g + 16 * i)
+                     : "memory");
+}
+// N consecutive floats of a per-column vector, the same address in every lane (one L1 transaction
+// per 16 bytes, broadcast).
+template <int N>
+__device__ __forceinline__ void ld_uniform(float* r, const float* g) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+}
+// Row statistics from the partials the producing epilogue left: equal-sized spans, so
+// mean = avg(mean_i), M2 = sum M2_i + span * sum (mean_i - mean)^2 (Chan et al.).  Returns
+// rstd and -rstd * mean.
+__device__ __forceinline__ void row_mean_rstd(const float2* st, int nspan, bool ok, float eps, float& rstd,
+                                              float& nrm) {
+    rstd = 0.f;
+    nrm = 0.f;
+    if (!ok) return;
+    float4 t[6];
+    float ms = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (2 * i < nspan) {
+            t[i] = __ldg(reinterpret_cast<const float4*>(st) + i);
+            ms += t[i].x + t[i].z;
+        }
+    const float mean = ms / static_cast<float>(nspan);
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (2 * i < nspan) {
+            const float d0 = t[i].x - mean, d1 = t[i].z - mean;
+            m2 += (t[i].y + t[i].w) + static_cast<float>(LN_SPAN) * (d0 * d0 + d1 * d1);
+        }
+    rstd = rsqrtf(m2 / static_cast<float>(nspan * LN_SPAN) + eps);
+    nrm = -rstd * mean;
 }
 
 // One 16-byte chunk of a 128-byte staging row under the 128B swizzle TMA expects.
@@ -133,7 +200,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if constexpr (EPI <= EPI_SWIGLU_BF16) tma_prefetch_desc(&tmC);
+        if constexpr (C::BOXES == 1 && EPI != EPI_BIAS_GELU_F32 && EPI != EPI_BIAS_F32) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -224,7 +291,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         uint8_t* box = stg_all + (warp - 4) * BOXES * BOX_BYTES;
         int acc = 0;
         uint32_t acc_phase = 0;
-        float xres[EPI == EPI_RESID_F32 ? 64 : 1];    // residual epilogue: two 32-float register sets of x
+        constexpr bool RESID = EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN;
+        float xres[RESID ? 64 : 1];                   // residual epilogue: two 32-float register sets of x
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int nb = tile % p.n_tiles;
             const int n0 = nb * BN + half * (BN / 2);
@@ -291,7 +359,84 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     tma_store_2d(&tmC, box, nb * (BN / 2) + half * 64, row_base);
                     bulk_commit_group();
                 }
-            } else if constexpr (EPI == EPI_RESID_F32) {
+            } else if constexpr (EPI == EPI_STORE_BF16_LN) {
+                // out = rstd * acc + (b[n] - rstd * mean * c[n]); the row statistics are fetched
+                // while the main loop of this tile is still running
+                float rstd, nrm;
+                row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
+                              row_base + lane < p.M, p.ln_eps, rstd, nrm);
+                mbar_wait(&tfull[acc], acc_phase);
+                tcgen05_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < (BN / 2) / 64; ++c) {
+                    if (lane == 0) bulk_wait_group_read<0>();     // the previous store has read the box
+                    __syncwarp();
+#pragma unroll 1
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t v[32];
+                        float cs[32], bs[32];
+                        tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
+                        ld_uniform<32>(cs, p.colsum + n0 + c * 64 + hh * 32);
+                        ld_uniform<32>(bs, p.bias + n0 + c * 64 + hh * 32);
+                        tmem_ld_wait();
+                        float y[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), rstd, fmaf(nrm, cs[j], bs[j]));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            st_swz16(box, lane, hh * 4 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
+                                     pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
+                                     pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmC, box, n0 + c * 64, row_base);
+                        bulk_commit_group();
+                    }
+                }
+            } else if constexpr (EPI == EPI_SWIGLU_BF16_LN) {
+                float rstd, nrm;
+                row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
+                              row_base + lane < p.M, p.ln_eps, rstd, nrm);
+                mbar_wait(&tfull[acc], acc_phase);
+                tcgen05_fence_after();
+                const uint32_t t_gate = tmem_base + acc * ACC_STRIDE + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
+                const float* cg = p.colsum + nb * BN + half * 64;       // gate columns of this warp; up = +BN/2
+                const float* bg = p.bias + nb * BN + half * 64;
+                if (lane == 0) bulk_wait_group_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {                           // 16 output columns at a time
+                    uint32_t g[16], u[16];
+                    float c0[16], b0[16], c1[16], b1[16];
+                    tmem_ld_32x32b_x16(t_gate + h * 16, g);
+                    tmem_ld_32x32b_x16(t_gate + BN / 2 + h * 16, u);
+                    ld_uniform<16>(c0, cg + h * 16);
+                    ld_uniform<16>(b0, bg + h * 16);
+                    ld_uniform<16>(c1, cg + BN / 2 + h * 16);
+                    ld_uniform<16>(b1, bg + BN / 2 + h * 16);
+                    tmem_ld_wait();
+                    float y[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float yg = fmaf(__uint_as_float(g[j]), rstd, fmaf(nrm, c0[j], b0[j]));
+                        const float yu = fmaf(__uint_as_float(u[j]), rstd, fmaf(nrm, c1[j], b1[j]));
+                        y[j] = silu_fast(yg) * yu;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        st_swz16(box, lane, h * 2 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
+                                 pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
+                                 pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, box, nb * (BN / 2) + half * 64, row_base);
+                    bulk_commit_group();
+                }
+            } else if constexpr (RESID) {
                 // residual stream update x = x + acc / scale, entirely in registers: thread = row,
                 // one 32-column chunk of a row is one 128-byte line, moved as four 256-bit
                 // loads/stores.  Nothing touches shared memory here, which matters because the main
@@ -320,6 +465,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 const bool ok_next = nt < num_tiles && row_ok(nt);
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
+                // EPI_RESID_F32_LN: statistics of this thread's 128 columns of the updated row,
+                // shifted by the first element so that sum((x-k)^2) - sum(x-k)^2/n does not cancel
+                float st_shift = 0.f, st_s = 0.f, st_q = 0.f;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     float* xr = (c & 1) ? xres + 32 : xres;
@@ -329,10 +477,31 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
 #pragma unroll
                     for (int j = 0; j < 32; ++j) xr[j] = fmaf(__uint_as_float(v[j]), inv, xr[j]);
                     if (ok) st_row128(chunk_ptr(tile, c), xr);
+                    if constexpr (EPI == EPI_RESID_F32_LN) {
+                        if (c == 0) st_shift = xr[0];
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = xr[j] - st_shift;
+                            st_s += d;
+                            st_q = fmaf(d, d, st_q);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(xr[2 * j], xr[2 * j + 1]);
+                        if (ok) st_row64(p.xb_out + (chunk_ptr(tile, c) - xg), pk);
+                    }
                     if (c + 2 < NCH) {
                         if (ok) ld_row128(xr, chunk_ptr(tile, c + 2));
                     } else if (ok_next) {
                         ld_row128(xr, chunk_ptr(nt, c + 2 - NCH));
+                    }
+                }
+                if constexpr (EPI == EPI_RESID_F32_LN) {
+                    if (ok) {
+                        const long long row = static_cast<long long>(row_base + lane);
+                        const float sm = st_s * (1.0f / LN_SPAN);
+                        p.stats_out[row * (p.N / LN_SPAN) + nb * (BN / LN_SPAN) + half] =
+                            make_float2(st_shift + sm, st_q - st_s * sm);
                     }
                 }
             } else {
@@ -373,7 +542,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (EPI <= EPI_SWIGLU_BF16) {
+        if constexpr (C::BOXES == 1 && EPI != EPI_BIAS_GELU_F32 && EPI != EPI_BIAS_F32) {
             if (lane == 0) bulk_wait_group<0>();                  // stores complete before exit
         }
     }

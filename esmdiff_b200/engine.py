@@ -230,6 +230,26 @@ class Engine:
                                            out.stride(0), _ptr(bias), float(scale), _stream()))
         return out
 
+    def op_gemm_ln(self, epilogue: int, a, w, out, bias=None, scale=1.0, stats_in=None, colsum=None,
+                   stats_out=None, xb_out=None):
+        """LayerNorm-folded epilogues 5/6/7 (gemm.cuh)."""
+        M, K = a.shape
+        N = w.shape[0]
+        self._check(self.L.esmdiff_op_gemm_ln(self.h, epilogue, _ptr(a), _ptr(w), M, N, K, _ptr(out),
+                                              out.stride(0), _ptr(bias), float(scale), _ptr(stats_in),
+                                              _ptr(colsum), _ptr(stats_out), _ptr(xb_out), _stream()))
+        return out
+
+    def op_fold_layernorm(self, w, gamma, beta=None, swiglu_hidden=0):
+        rows, cols = w.shape
+        dst = torch.empty(rows, cols, dtype=torch.bfloat16, device=w.device)
+        colsum = torch.empty(rows, dtype=torch.float32, device=w.device)
+        bias = torch.empty(rows, dtype=torch.float32, device=w.device)
+        self._check(self.L.esmdiff_op_fold_layernorm(self.h, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(dst),
+                                                     _ptr(colsum), _ptr(bias), rows, cols,
+                                                     int(swiglu_hidden), _stream()))
+        return dst, colsum, bias
+
     def op_layernorm(self, x, w, b=None):
         M, D = x.shape
         y = torch.empty(M, D, dtype=torch.bfloat16, device=x.device)

@@ -140,6 +140,21 @@ int esmdiff_profile_read(esmdiff_ctx* ctx, int kind, double* ms, double* work, i
 int esmdiff_op_gemm(esmdiff_ctx* ctx, int epilogue, const void* a_bf16_dev, const void* w_bf16_dev,
                     int M, int N, int K, void* out_dev, int64_t ldo, const float* bias_dev,
                     float scale, void* stream);
+/* The LayerNorm-folded epilogues (the block pre-LNs of esm UnifiedTransformerBlock, applied as
+ * LN(x) W^T = rstd (x (gamma.W)^T - mean colsum(gamma.W)) + beta W^T):
+ *   5 store bf16 with row statistics, 6 resid fp32 + bf16 copy of the new rows (xb_out [M,N]) +
+ *   partial statistics (stats_out, float2 [M, N/128]), 7 SwiGLU bf16 with row statistics.
+ *   stats_in: float2 [M, K/128] (mean, M2) per 128-column span of the A rows; colsum/bias: [N]. */
+int esmdiff_op_gemm_ln(esmdiff_ctx* ctx, int epilogue, const void* a_bf16_dev, const void* w_bf16_dev,
+                       int M, int N, int K, void* out_dev, int64_t ldo, const float* bias_dev,
+                       float scale, const void* stats_in_dev, const float* colsum_dev,
+                       void* stats_out_dev, void* xb_out_dev, void* stream);
+/* dst bf16 [rows, cols] = W * gamma (columns), colsum[rows] = row sums of dst, bias[rows] = W beta
+ * (beta may be NULL); optional SwiGLU row interleave as esmdiff_op_convert_bf16. */
+int esmdiff_op_fold_layernorm(esmdiff_ctx* ctx, const float* w_dev, const float* gamma_dev,
+                              const float* beta_dev, void* dst_bf16_dev, float* colsum_dev,
+                              float* bias_dev, int64_t rows, int64_t cols, int swiglu_hidden,
+                              void* stream);
 /* y bf16 [M,D] = LayerNorm(x fp32 [M,D]) * w + b (b may be NULL), eps 1e-5. */
 int esmdiff_op_layernorm(esmdiff_ctx* ctx, const float* x_dev, const float* w_dev,
                          const float* b_dev, void* y_bf16_dev, int M, int D, void* stream);

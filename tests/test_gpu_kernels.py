@@ -117,6 +117,66 @@ def test_gemm_linearity_full_size(engine):
     check(once, (a.float() @ w.float().T) / 2.0, 2e-5)
 
 
+def _combine_stats(stats, D):
+    """(mean, M2) partials over 128-column spans -> row mean, biased variance (Chan et al.)."""
+    mean_i, m2_i = stats[..., 0].double(), stats[..., 1].double()
+    mean = mean_i.mean(-1)
+    m2 = m2_i.sum(-1) + 128.0 * ((mean_i - mean[:, None]) ** 2).sum(-1)
+    return mean, m2 / D
+
+
+@pytest.mark.parametrize("M,D,F_h", [(1000, 1536, 4096), (130, 256, 768), (16254, 1536, 4096)])
+def test_gemm_layernorm_folded_epilogues(engine, M, D, F_h):
+    """The block pre-LayerNorms folded through the GEMMs (gemm.cuh epilogues 5/6/7) against
+    torch: residual update + bf16 copy + partial statistics, then LN(x) @ W^T with gamma folded
+    into W, non-trivial gamma/beta, a row offset and an outlier channel (real ESM3 streams carry
+    |x| ~ 1e4 in single channels)."""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    a = torch.randn(M, D, device=DEV, generator=g).bfloat16()
+    wo = (torch.randn(D, D, device=DEV, generator=g) / D ** 0.5).bfloat16()
+    x0 = torch.randn(M, D, device=DEV, generator=g) * 3 + 0.7
+    x0[:, 77] += 900.0                                           # outlier channel
+    x0[::7] -= 2.5                                               # row-dependent mean
+    x = x0.clone()
+    xb = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(M, D // 128, 2, device=DEV)
+    engine.op_gemm_ln(6, a, wo, x, scale=1.1547005, stats_out=stats, xb_out=xb)
+    engine.synchronize()
+    ref_x = x0 + (a.float() @ wo.float().T) / 1.1547005
+    check(x, ref_x, 2e-5)
+    assert torch.equal(xb, x.bfloat16())                         # the copy is the rounded new stream
+    mean, var = _combine_stats(stats, D)
+    assert float((mean - x.double().mean(-1)).abs().max()) < 1e-4
+    ref_var = x.double().var(-1, unbiased=False)
+    assert float(((var - ref_var).abs() / ref_var).max()) < 1e-5
+
+    gamma = 1.0 + 0.3 * torch.randn(D, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(D, device=DEV, generator=g)
+    wq = torch.randn(3 * D, D, device=DEV, generator=g) / D ** 0.5
+    ln = F.layer_norm(x, (D,), gamma, beta, 1e-5)
+    wq_f, cq, bq = engine.op_fold_layernorm(wq, gamma, beta)
+    assert torch.equal(wq_f, (wq * gamma).bfloat16())
+    qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=DEV)
+    engine.op_gemm_ln(5, xb, wq_f, qkv, bias=bq, stats_in=stats, colsum=cq)
+    engine.synchronize()
+    check(qkv, ln @ wq.T, 6e-3, 3e-2)                            # bf16 operands AND bf16 output
+
+    w1 = torch.randn(2 * F_h, D, device=DEV, generator=g) / D ** 0.5
+    w1_f, c1, b1 = engine.op_fold_layernorm(w1, gamma, beta, swiglu_hidden=F_h)
+    h = torch.empty(M, F_h, dtype=torch.bfloat16, device=DEV)
+    engine.op_gemm_ln(7, xb, w1_f, h, bias=b1, stats_in=stats, colsum=c1)
+    engine.synchronize()
+    z = ln @ w1.T
+    check(h, F.silu(z[:, :F_h]) * z[:, F_h:], 8e-3, 3e-2)
+    # against the stand-alone LayerNorm kernel + plain epilogue on the same inputs (the two product
+    # variants, ESMDIFF_LN=separate): same operands up to where the bf16 rounding is applied
+    xn = engine.op_layernorm(x, gamma, beta)
+    qkv2 = torch.empty_like(qkv)
+    engine.op_gemm(0, xn, wq.bfloat16(), qkv2)
+    engine.synchronize()
+    assert rel_fro(qkv, ln @ wq.T) < 1.5 * rel_fro(qkv2, ln @ wq.T) + 1e-4
+
+
 # ---------------------------------------------------------------------------------------------
 # row kernels
 # ---------------------------------------------------------------------------------------------

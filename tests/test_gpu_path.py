@@ -186,6 +186,50 @@ def test_inpainting_tiny(tiny_pair):
     assert len({tuple(r.tolist()) for r in out[:, 1:33]}) > 1      # samples differ
 
 
+def test_trained_like_layernorm_weights_both_variants():
+    """Default init has gamma = 1, beta = 0 in every LayerNorm, which would leave the LayerNorm
+    folding (gemm.cuh) and the q_ln/k_ln weights untested end to end: perturb them all, then the
+    folded path (default) and the stand-alone-kernel path (ESMDIFF_LN=separate) must both match
+    the fp32 oracle."""
+    import os
+    from conftest import TINY
+    from esmdiff_b200.engine import Dims, Engine
+    net, emb = esm3_ref.build_reference_model(esm3_ref.Esm3Dims(**TINY), seed=3)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for name, prm in net.named_parameters():
+            if prm.dim() == 1 and ("layernorm" in name or "ffn.0" in name or "q_ln" in name or "k_ln" in name
+                                   or "norm" in name or "structure_head.2" in name):
+                if name.endswith("weight"):
+                    prm.mul_(1.0 + 0.25 * torch.randn(prm.shape, generator=g))
+                else:
+                    prm.add_(0.2 * torch.randn(prm.shape, generator=g))
+    sd = esm3_ref.full_state_dict(net, emb)
+    B, T = 3, 70
+    seq = make_seq(B, T, seed=5)
+    xt = torch.randint(0, 4096, (B, T), generator=g)
+    xt[torch.rand(B, T, generator=g) < 0.6] = MASK
+    with torch.no_grad():
+        cond = emb(torch.tensor([0.7]))[0]
+        ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond[None, None].expand(B, T, -1))
+    errs = {}
+    for mode in ("fold", "separate"):
+        os.environ["ESMDIFF_LN"] = mode
+        try:
+            eng = Engine(Dims(**TINY))
+        finally:
+            os.environ.pop("ESMDIFF_LN")
+        eng.load_state_dict(sd)
+        logits, embd = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(0.7), want_embeddings=True)
+        eng.synchronize()
+        errs[mode] = (rel_fro(embd.cpu(), ref.embeddings), rel_fro(logits.cpu(), ref.structure_logits))
+        eng.close()
+    print(f"\n[LN variants] (embeddings, logits) rel_fro: {errs}")
+    for e_emb, e_log in errs.values():
+        assert e_emb < 1e-2 and e_log < 2e-2
+    assert errs["fold"][1] < 1.5 * errs["separate"][1] + 1e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # ESM3-open-sized model (d=1536, 48 layers, 24 heads)
 # ---------------------------------------------------------------------------------------------

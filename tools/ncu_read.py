@@ -36,6 +36,10 @@ def main():
     for w in WANT:
         if w in ix:
             print(f"{w:75s} {units[ix[w]]:12s} {[r[ix[w]] for r in data]}")
+    st = sorted(((float(data[which][i].replace(",", "") or 0), h.replace("smsp__pcsamp_warps_issue_stalled_", ""))
+                 for h, i in ix.items() if h.startswith("smsp__pcsamp_warps_issue_stalled_")
+                 and not h.endswith("_not_issued")), reverse=True)[:10]
+    print("stall samples (kernel", which, "):", st)
     src = list(csv.reader(io.StringIO(run(["-i", rep, "--page", "source", "--csv"]))))
     blocks, cur = [], None
     for r in src:
@@ -46,9 +50,11 @@ def main():
             cur["hdr"] = r
         elif cur is not None and r:
             cur["rows"].append(r)
-    b = blocks[which]
+    name = data[which][ix["Kernel Name"]][:40]
+    cands = [b for b in blocks if "rows" in b and b["rows"] and name[:25] in b["name"]]
+    b = cands[0] if cands else blocks[which]
     ix = {h: i for i, h in enumerate(b["hdr"])}
-    S = ix["# Samples"]
+    S = ix["# Samples"] if "# Samples" in ix else ix["Warp Stall Sampling (All Samples)"]
     stalls = [h for h in b["hdr"] if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(int(r[S]) for r in b["rows"])
     agg = {h: sum(int(r[ix[h]]) for r in b["rows"]) for h in stalls}

@@ -32,5 +32,10 @@ for _ in range(3):
     e.op_gemm(1, att, wo, x, scale=1.1547)
     e.op_gemm(2, xn, w1, h)
     e.op_gemm(1, hb, w2, x, scale=1.1547)
+    # sampling kernel: about half of the rows still masked (step ~12 of 25), library Philox uniforms
+    logits = torch.randn(B, T, 4101, device=dev, generator=g)
+    xt = torch.where(torch.rand(B, T, device=dev, generator=g) < 0.5, 4096,
+                     torch.randint(0, 4096, (B, T), device=dev, generator=g)).to(torch.int64)
+    e.sample_step(xt, logits, None, 0.52, 0.48, seed=1, step=12)
 e.synchronize()
 print("done", e.launch_count)
