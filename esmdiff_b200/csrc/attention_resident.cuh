@@ -70,7 +70,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint64_t* q_empty = bars + 2;                         // [2]
     uint64_t* s_full = bars + 4;                          // [2]  MMA -> softmax
     uint64_t* p_full = bars + 6;                          // [2]  softmax (128 threads) -> MMA
-    uint64_t* pv_done = bars + 8;                         // 1    completes once per step
+    uint64_t* pv_done = bars + 8;                         // 1    P V of step nsteps-2 retired (no S follows it)
     uint64_t* o_free = bars + 9;                          // 1    completes once per query tile
     uint64_t* o_full = bars + 10;                         // 1    last PV of a query tile retired
     uint64_t* k_full = bars + 11;                         // [MAX_KV_TILES], single use
@@ -194,8 +194,11 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                         for (int k = 0; k < ksteps; ++k)
                             umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(pv_done);
+                    // every tcgen05.commit stalls this thread ~200 clk (tools/mma_bench.cu): the "P V of
+                    // step i retired" signal the rare rescale path needs rides on the commit of S_{i+2},
+                    // issued right behind it; only the P Vs that no S follows commit their own
                     if (last) umma_commit(o_full);
+                    else if (s_i >= nsteps) umma_commit(pv_done);
                 }
                 __syncwarp();
                 if (s_i < nsteps) issue_s();              // overwrites P_i's buffer: ordered after PV_i
@@ -283,7 +286,10 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                             // raise the running max: rescale O and l in TMEM once PV_{i-1} has retired
                             const float m_new = need ? mx : m_run;
                             const float f = fast_exp2((m_run - m_new) * sc);
-                            mbar_wait(pv_done, (i - 1) & 1);
+                            // P V of step i-1 retired: implied by the commit of S_{i+1} (issued after it);
+                            // the very last step has no S_{i+1} and waits for the single pv_done commit
+                            if (i + 1 < nsteps) mbar_wait(&s_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+                            else mbar_wait(pv_done, 0);
                             tcgen05_fence_after();
                             l_run *= f;
 #pragma unroll 1

@@ -539,7 +539,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[acc]), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[acc]), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if constexpr (C::BOXES == 1 && EPI != EPI_BIAS_GELU_F32 && EPI != EPI_BIAS_F32) {

@@ -133,6 +133,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without release semantics.  For barriers that only order tcgen05 (TMEM) accesses, which the
+// tcgen05.fence pair already orders: a .release arrive after st.global compiles to MEMBAR.ALL.GPU +
+// ERRBAR and waits for every outstanding store of the thread (ncu r1f: 15 % of the residual
+// epilogue's samples).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // 2-D tile load issued by either CTA of a pair; completion bytes land on the mbarrier at
 // `bar_cluster_addr` (the leader CTA's barrier).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,

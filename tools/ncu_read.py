@@ -50,9 +50,15 @@ def main():
             cur["hdr"] = r
         elif cur is not None and r:
             cur["rows"].append(r)
-    name = data[which][ix["Kernel Name"]][:40]
-    cands = [b for b in blocks if "rows" in b and b["rows"] and name[:25] in b["name"]]
-    b = cands[0] if cands else blocks[which]
+    # the source page lists every sampled launch twice (two views): collapse the pairs
+    dedup = []
+    for blk in blocks:
+        prev = dedup[-1] if dedup else None
+        if prev and prev["name"] == blk["name"] and len(prev["rows"]) == len(blk["rows"]) and not prev.get("paired"):
+            prev["paired"] = True
+            continue
+        dedup.append(blk)
+    b = dedup[which]
     ix = {h: i for i, h in enumerate(b["hdr"])}
     S = ix["# Samples"] if "# Samples" in ix else ix["Warp Stall Sampling (All Samples)"]
     stalls = [h for h in b["hdr"] if h.startswith("stall_") and "Not Issued" not in h]
