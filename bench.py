@@ -54,6 +54,18 @@ def forward_flops(B: int, T: int) -> float:
     return float(B) * T * (48 * (56_623_104 + 6144 * T) + 17_316_864)
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel family (the tcgen05 GEMMs: QKV, out_proj, W1, W2 --
+    one launch each per block) from the newest committed `ncu --set full` summary
+    (tools/ncu_summary.py -> profiles/*_ncu_full.json).  None when no capture is committed."""
+    files = sorted((ROOT / "profiles").glob("*_ncu_full.json"))
+    if not files:
+        return None, None
+    d = json.loads(files[-1].read_text())
+    g = [k["dram_bytes"] for k in d["kernels"] if "gemm_bf16_tn_kernel" in k["kernel"]]
+    return (sum(g) / len(g), files[-1].name) if g else (None, None)
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -277,6 +289,7 @@ def gpu_bench(args):
     e2e_value = tokens_per_step / (e2e_s / args.steps)
 
     peak_tf, peak_gbs, how = measured_peaks()
+    traffic, traffic_src = ncu_traffic()
     gemm = [prof[k] for k in ("gemm_store_bf16", "gemm_resid_f32", "gemm_swiglu", "gemm_bias_gelu", "gemm_bias")]
     g_ms, g_fl, g_n = (sum(x[i] for x in gemm) for i in range(3))
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
@@ -293,7 +306,7 @@ def gpu_bench(args):
                 "frac": round(achieved / peak_tf, 4), "peak_source": f"{how} bf16 sustained",
                 "launches": g_n, "avg_launch_ms": round(g_ms / max(g_n, 1), 4),
                 "flops_per_launch": g_fl / max(g_n, 1), "share_of_step": round(g_ms / ms_total, 4),
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "whole_job": {"algorithmic_tflop_per_step": round(fwd_flops / 1e12, 1),
                               "tflops": round(fwd_flops / (ms_per_step * 1e-3) / 1e12, 1),
                               "frac": round(fwd_flops / (ms_per_step * 1e-3) / 1e12 / peak_tf, 4)},

@@ -32,16 +32,19 @@ constexpr int MAX_KV_TILES = 12;            // T <= 768
 constexpr int Q_BYTES = BQ * DH * 2;        // 16 KiB
 constexpr int KV_TILE_BYTES = BKV * DH * 2; // 8 KiB
 constexpr int BAR_BYTES = 512;
-constexpr int THREADS = 192;                // warps 0-3 softmax, 4 TMA, 5 MMA
+constexpr int THREADS = 256;                // warps 0-3 softmax, 4 TMA, 5 MMA, 6-7 leftover query rows (CUDA cores)
+constexpr int MAX_LEFT = 2;                 // T mod 128 <= 2 (BOS/EOS around L = 128 k residues): no tensor tile for them
 constexpr int TMEM_COLS = 256;              // S0 [0,64) S1 [64,128) O [128,192)
 constexpr int COL_O = 128;
 constexpr float RESCALE_LOG2 = 8.0f;        // lazy rescale threshold: p <= 2^8
 
 struct Params {
     int B, T, H;
-    int nq;                     // ceil(T / 128)
+    int nq;                     // query tiles of 128 rows on the tensor path: ceil(T / 128), or floor when n_left > 0
+    int n_left;                 // 0..MAX_LEFT trailing query rows done by warps 6-7 on CUDA cores
     int nkv;                    // ceil(T / 64)
     int tail_cols;              // width of the last kv tile: multiple of 16 in [16, 64]
+    const __nv_bfloat16* qkv;   // [B*T, 3*H*64] (the leftover warps read their query rows directly)
     __nv_bfloat16* ctx;         // [B*T, H*64]
     float scale_log2;           // (1/sqrt(64)) * log2(e)
 };
@@ -49,8 +52,96 @@ struct Params {
 __host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
     return (nkv - 1) * KV_TILE_BYTES + tail_cols * 128;
 }
+__host__ __device__ inline int left_bytes(int nkv) { return MAX_LEFT * nkv * BKV * 4; }   // fp32 p per leftover row
 __host__ inline int smem_bytes(int nkv, int tail_cols) {
-    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + BAR_BYTES;
+    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + BAR_BYTES + left_bytes(nkv);
+}
+
+// One trailing query row on CUDA cores (one warp), K and V read from the swizzled shared-memory
+// tiles the tensor path uses.  T = L + 2 tokens puts exactly two rows (the last residue and EOS)
+// past the last full 128-row tile whenever L is a multiple of 128 -- every configuration the path
+// is quoted on -- and a tensor tile for them costs a third of the kernel at T = 258 (5 of 15
+// MMA/softmax steps with 2 of 128 rows live).  Scores: lane = key (k = lane + 32 m), q in
+// registers; P V: lane = two output dims, p broadcast from shared memory.  fp32 throughout.
+__device__ __forceinline__ void leftover_row(const __nv_bfloat16* __restrict__ qrow, __nv_bfloat16* __restrict__ orow,
+                                             const uint8_t* sK, const uint8_t* sV, float* pf, int T, float sc,
+                                             uint64_t* k_full, uint64_t* v_full, int nkv, int lane) {
+    // q: every lane needs all 64 dims -> 8 x 16-byte loads of the same 128-byte row
+    float q[DH];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(qrow);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 v = __ldg(src + c);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                q[8 * c + 2 * e] = __uint_as_float(w[e] << 16);
+                q[8 * c + 2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+            }
+        }
+    }
+    for (int j = 0; j < nkv; ++j) mbar_wait(&k_full[j], 0);
+    const int nk = (T + 31) >> 5;                      // keys per lane
+    float mx = -INFINITY;
+    for (int m = 0; m < nk; ++m) {
+        const int k = m * 32 + lane;
+        const int kk = k < T ? k : T - 1;              // clamp: rows past T may not be loaded
+        const uint8_t* rowp = sK + (kk >> 6) * KV_TILE_BYTES + (kk & 63) * 128;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(rowp + ((c ^ (kk & 7)) << 4));
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a0 = fmaf(q[8 * c + 2 * e], __uint_as_float(w[e] << 16), a0);
+                a1 = fmaf(q[8 * c + 2 * e + 1], __uint_as_float(w[e] & 0xffff0000u), a1);
+            }
+        }
+        const float sv = k < T ? (a0 + a1) * sc : -INFINITY;
+        pf[k] = sv;                                    // pf holds nkv * 64 >= nk * 32 floats
+        mx = fmaxf(mx, sv);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float l = 0.f;
+    for (int m = 0; m < nk; ++m) {
+        const int k = m * 32 + lane;
+        const float pv = fast_exp2(pf[k] - mx);        // exp2(-inf) = 0 for the padding keys
+        pf[k] = pv;
+        l += pv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) mbar_wait(&v_full[j], 0);
+    // out[2 lane, 2 lane + 1] = sum_k p[k] V[k][2 lane, 2 lane + 1]
+    int off[8];                                        // byte offset of my dim pair inside row r, r & 7 = i
+#pragma unroll
+    for (int i = 0; i < 8; ++i) off[i] = i * 128 + ((((lane >> 2) ^ i) << 4) | ((lane & 3) << 2));
+    float o0 = 0.f, o1 = 0.f;
+    const int k8 = T >> 3;
+    for (int g = 0; g < k8; ++g) {                     // 8 keys per trip: rows 8 g .. 8 g + 7 of one tile
+        const uint8_t* base = sV + (g >> 3) * KV_TILE_BYTES + (g & 7) * 1024;
+        const float4 pa = *reinterpret_cast<const float4*>(pf + 8 * g);
+        const float4 pb = *reinterpret_cast<const float4*>(pf + 8 * g + 4);
+        const float pp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(base + off[i]);
+            o0 = fmaf(pp[i], __uint_as_float(v << 16), o0);
+            o1 = fmaf(pp[i], __uint_as_float(v & 0xffff0000u), o1);
+        }
+    }
+    for (int k = k8 * 8; k < T; ++k) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(sV + (k >> 6) * KV_TILE_BYTES + (k & 63) * 128 +
+                                                             ((((lane >> 2) ^ (k & 7)) << 4) | ((lane & 3) << 2)));
+        o0 = fmaf(pf[k], __uint_as_float(v << 16), o0);
+        o1 = fmaf(pf[k], __uint_as_float(v & 0xffff0000u), o1);
+    }
+    const float inv = 1.0f / l;
+    reinterpret_cast<uint32_t*>(orow)[lane] = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
 __global__ void __launch_bounds__(THREADS, 2)
@@ -76,6 +167,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint64_t* k_full = bars + 11;                         // [MAX_KV_TILES], single use
     uint64_t* v_full = k_full + MAX_KV_TILES;             // [MAX_KV_TILES], single use
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_full + MAX_KV_TILES);
+    float* left_p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [MAX_LEFT][nkv * 64]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -203,6 +295,15 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                 __syncwarp();
                 if (s_i < nsteps) issue_s();              // overwrites P_i's buffer: ordered after PV_i
             }
+        }
+    } else if (warp >= 6) {
+        // ===================== trailing query rows past the last full tile =====================
+        const int lw = warp - 6;
+        if (lw < p.n_left) {
+            const int t = p.nq * BQ + lw;
+            leftover_row(p.qkv + static_cast<long long>(row0 + t) * 3 * D + h * DH,
+                         p.ctx + static_cast<long long>(row0 + t) * D + h * DH, sK, sV, left_p + lw * nkv * BKV, p.T,
+                         p.scale_log2, k_full, v_full, nkv, lane);
         }
     } else {
         // ===================== softmax / output warps: thread = query row =====================

@@ -59,7 +59,8 @@ struct esmdiff_ctx {
     std::string err;
     int64_t launches = 0;
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
-                               // (ESMDIFF_ATTN=stream), 3 = experimental Q-in-TMEM / 8-softmax-warp kernel (qtmem; slower)
+                               // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles),
+                               // 3 = experimental Q-in-TMEM / 8-softmax-warp kernel (qtmem; slower)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
     EncodeTiledFn encode = nullptr;
 
@@ -368,6 +369,12 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     attn2::Params p;
     p.B = B; p.T = T; p.H = H;
     p.nq = (T + attn2::BQ - 1) / attn2::BQ;
+    p.n_left = 0;
+    if (T > attn2::BQ && T % attn2::BQ != 0 && T % attn2::BQ <= attn2::MAX_LEFT && c->attn_variant != 2) {
+        p.n_left = T % attn2::BQ;                  // T = 128 k + 2 (BOS/EOS): no tensor tile for two rows
+        p.nq = T / attn2::BQ;
+    }
+    p.qkv = qkv;
     p.nkv = nkv;
     p.tail_cols = tail_cols;
     p.ctx = out;
@@ -657,7 +664,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->layers.resize(cfg->n_layers);
     if (const char* e = getenv("ESMDIFF_ATTN"))
-        c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "qtmem") == 0 ? 3 : 0;
+        c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "tiles") == 0 ? 2 : strcmp(e, "qtmem") == 0 ? 3 : 0;
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

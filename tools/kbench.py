@@ -70,7 +70,7 @@ def bench_gemm(flush):
 
 def bench_attn(flush):
     g = torch.Generator(device="cuda").manual_seed(5)
-    engs = {"resident": engine(), "qtmem": engine(ESMDIFF_ATTN="qtmem")}
+    engs = {"resident": engine(), "tiles": engine(ESMDIFF_ATTN="tiles")}
     # correctness first
     for (B, T, H) in [(1, 64, 1), (2, 60, 4), (2, 130, 4), (3, 258, 24), (1, 514, 4), (2, 129, 3), (5, 1, 2), (1, 700, 2)]:
         D = H * 64

@@ -24,14 +24,21 @@ x = torch.randn(M, 1536, device=dev, generator=g)
 qkv = torch.empty(M, 4608, dtype=torch.bfloat16, device=dev)
 h = torch.empty(M, 4096, dtype=torch.bfloat16, device=dev)
 ones = torch.ones(1536, device=dev)
+# the product path folds the block pre-LayerNorms through the GEMMs (epilogues 5/6/7, gemm.cuh)
+wq_f, cq, bq = e.op_fold_layernorm(wq.float(), ones, ones)
+w1_f, c1, b1 = e.op_fold_layernorm(w1.float(), ones, ones, swiglu_hidden=4096)
+xb = torch.empty(M, 1536, dtype=torch.bfloat16, device=dev)
+stats = torch.zeros(M, 12, 2, device=dev)
+att0 = torch.randn(M, 1536, device=dev, generator=g).bfloat16()
+e.op_gemm_ln(6, att0, wo, x, scale=1.1547, stats_out=stats, xb_out=xb)      # fills xb / stats
+e.synchronize()
 for _ in range(3):
-    xn = e.op_layernorm(x, ones, ones)
-    e.op_gemm(0, xn, wq, qkv)
+    e.op_gemm_ln(5, xb, wq_f, qkv, bias=bq, stats_in=stats, colsum=cq)
     e.op_qk_norm_rope(qkv, ones, ones, B, T)
     att = e.op_attention(qkv, B, T, H)
-    e.op_gemm(1, att, wo, x, scale=1.1547)
-    e.op_gemm(2, xn, w1, h)
-    e.op_gemm(1, hb, w2, x, scale=1.1547)
+    e.op_gemm_ln(6, att, wo, x, scale=1.1547, stats_out=stats, xb_out=xb)
+    e.op_gemm_ln(7, xb, w1_f, h, bias=b1, stats_in=stats, colsum=c1)
+    e.op_gemm_ln(6, hb, w2, x, scale=1.1547, stats_out=stats, xb_out=xb)
     # sampling kernel: about half of the rows still masked (step ~12 of 25), library Philox uniforms
     logits = torch.randn(B, T, 4101, device=dev, generator=g)
     xt = torch.where(torch.rand(B, T, device=dev, generator=g) < 0.5, 4096,

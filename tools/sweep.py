@@ -1,0 +1,78 @@
+"""BASELINE config 5: batch sweep L in {128, 256, 512, 1024} x num_samples in {1, 8, 64, 512},
+25 steps + noise removal, random-init ESM3-open-sized weights -> roofline table.
+
+    gpurun -- python tools/sweep.py > profiles/<round>_sweep.md     (one GPU, ~3 min)
+
+Per cell: structure-tokens/s (device-resident inputs, CUDA events, one warm run per shape class),
+whole-job TFLOP/s on the algorithmic FLOPs of SURVEY.md 8(d) and its fraction of the measured
+sustained bf16 peak, share of the time in the tcgen05 GEMMs / attention, HBM GB/s of the sampling
+kernel.  The reference's CPU path beside it is bench.py's cpu_baseline (one number per box)."""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from esmdiff_b200.engine import Dims, Engine  # noqa: E402
+from esmdiff_b200.sampling import chunk_sizes_b200  # noqa: E402
+from esmdiff_b200.synthetic import random_state_dict  # noqa: E402
+from esmdiff_b200.tokenization import synthetic_sequence_tokens  # noqa: E402
+
+
+def fwd_flops(B, T):
+    return float(B) * T * (48 * (56_623_104 + 6144 * T) + 17_316_864)
+
+
+def main():
+    dev = torch.device("cuda")
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    dims = Dims()
+    eng = Engine(dims)
+    eng.load_state_dict(random_state_dict(dims, device=dev, seed=0))
+    steps = 25
+    sched = eng.schedule(steps)
+    print(f"B200 sweep, {steps} steps + noise removal, bf16 tcgen05 path; peak = {peak} TFLOP/s (measured sustained bf16)\n")
+    print("| L | samples | batches | ms | tokens/s | TFLOP/s | % of peak | GEMM share | attention share | GEMM TFLOP/s | attention TFLOP/s | sampler GB/s |")
+    print("|---:|---:|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for L in (128, 256, 512, 1024):
+        T = L + 2
+        seq = synthetic_sequence_tokens(L, seed=0).to(dev)
+        for N in (1, 8, 64, 512):
+            chunks = chunk_sizes_b200(T, N)
+
+            def job(seed):
+                outs = [eng.ddpm_sample(seq[None].expand(b, T).contiguous(), None, steps, *sched, seed=seed + i)
+                        for i, b in enumerate(chunks)]
+                return torch.cat(outs)
+
+            if N in (1, 8):
+                job(1)                                    # warm (allocations, tensor maps)
+            torch.cuda.synchronize()
+            eng.profile(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tok = job(7)
+            e1.record()
+            torch.cuda.synchronize()
+            eng.synchronize()
+            eng.profile(False)
+            ms = e0.elapsed_time(e1)
+            prof = eng.profile_read()
+            assert tok.shape == (N, T) and int((tok == 4096).sum()) == 0
+            flops = (steps + 1) * sum(fwd_flops(b, T) for b in chunks)
+            g = [prof[k] for k in prof if k.startswith("gemm")]
+            g_ms, g_fl = sum(x[0] for x in g), sum(x[1] for x in g)
+            a_ms, a_fl, _ = prof["attention"]
+            s_ms, s_b, _ = prof["sampler"]
+            print(f"| {L} | {N} | {chunks if len(chunks) < 4 else str(len(chunks)) + ' x ' + str(chunks[0])} | {ms:.1f} | "
+                  f"{N * L / ms * 1e3:.0f} | {flops / ms / 1e9:.0f} | {100 * flops / ms / 1e9 / peak:.1f} | "
+                  f"{100 * g_ms / ms:.1f} | {100 * a_ms / ms:.1f} | {g_fl / g_ms / 1e9:.0f} | {a_fl / a_ms / 1e9:.0f} | "
+                  f"{s_b / s_ms / 1e6:.0f} |", flush=True)
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
