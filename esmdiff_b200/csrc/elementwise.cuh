@@ -71,7 +71,7 @@ layernorm_f32_to_bf16_kernel(const float* __restrict__ x, const float* __restric
 // the rotate-half partner of column o is o +- 32, i.e. lane +- 4).
 // ---------------------------------------------------------------------------------------------
 template <int MAXC>
-__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, 4)
 qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ q_w,
                          const float* __restrict__ k_w, const float* __restrict__ cos_t,
                          const float* __restrict__ sin_t, int M, int D, int T, float eps) {
@@ -93,42 +93,39 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
         sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w;
         sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
     }
-    // both rows (q and k) are requested before either is reduced: 12 x 16 B in flight per lane
-    uint4 raw[2][MAXC];
-#pragma unroll
-    for (int which = 0; which < 2; ++which)
-#pragma unroll
-        for (int i = 0; i < MAXC; ++i)
-            if (i < nc)
-                raw[which][i] = *reinterpret_cast<const uint4*>(
-                    qkv + static_cast<long long>(row) * 3 * D + which * D + i * 256 + lane * 8);
-#pragma unroll
+    // q, then k.  The values stay PACKED (bf16 pairs) in registers and are unpacked again in each of
+    // the three passes (one shift or mask per element): keeping fp32 copies of both rows cost 119
+    // registers = 16 warps per SM and 3.4 TB/s; this form fits four blocks (32 warps) per SM, and
+    // occupancy, not bytes in flight per warp, is what this kernel was short of.
+    auto lo = [](uint32_t w) { return __uint_as_float(w << 16); };
+    auto hi = [](uint32_t w) { return __uint_as_float(w & 0xffff0000u); };
+#pragma unroll 1
     for (int which = 0; which < 2; ++which) {
         __nv_bfloat16* base = qkv + static_cast<long long>(row) * 3 * D + which * D;
         const float* w = which == 0 ? q_w : k_w;
-        float v[MAXC][8];
+        uint4 rawq[MAXC];
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i)
+            if (i < nc) rawq[i] = *reinterpret_cast<const uint4*>(base + i * 256 + lane * 8);
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXC; ++i)
             if (i < nc) {
-                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw[which][i]);
+                const uint32_t r4[4] = {rawq[i].x, rawq[i].y, rawq[i].z, rawq[i].w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(h2[e]);
-                    v[i][2 * e] = f.x;
-                    v[i][2 * e + 1] = f.y;
-                    s += f.x + f.y;
-                }
+                for (int e = 0; e < 4; ++e) s += lo(r4[e]) + hi(r4[e]);
             }
         const float mean = warp_sum(s) / D;
         float q = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXC; ++i)
             if (i < nc) {
+                const uint32_t r4[4] = {rawq[i].x, rawq[i].y, rawq[i].z, rawq[i].w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float dlt = v[i][e] - mean;
-                    q += dlt * dlt;
+                for (int e = 0; e < 4; ++e) {
+                    const float d0 = lo(r4[e]) - mean, d1 = hi(r4[e]) - mean;
+                    q = fmaf(d0, d0, q);
+                    q = fmaf(d1, d1, q);
                 }
             }
         const float rstd = rsqrtf(warp_sum(q) / D + eps);
@@ -138,9 +135,13 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
                 const float4* w4 = reinterpret_cast<const float4*>(w + i * 256 + lane * 8);
                 const float4 wa = w4[0], wb = w4[1];
                 const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                const uint32_t r4[4] = {rawq[i].x, rawq[i].y, rawq[i].z, rawq[i].w};
                 float n[8], out[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) n[e] = (v[i][e] - mean) * rstd * ww[e];
+                for (int e = 0; e < 4; ++e) {
+                    n[2 * e] = (lo(r4[e]) - mean) * rstd * ww[2 * e];
+                    n[2 * e + 1] = (hi(r4[e]) - mean) * rstd * ww[2 * e + 1];
+                }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float partner = __shfl_xor_sync(0xffffffffu, n[e], 4);
