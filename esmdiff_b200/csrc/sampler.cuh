@@ -12,7 +12,8 @@ namespace esmdiff {
 namespace sampler {
 
 constexpr int THREADS = 256;
-constexpr int MAX_PER_THREAD = 17;           // ceil(4101 / 256); V <= 4352
+constexpr int MAX_PER_THREAD = 17;           // V <= 256 * 17 = 4352
+constexpr int GROUPS = 5;                    // a thread owns columns 4 (t + 256 k) .. + 3, k < 5: 5120 >= 4352
 constexpr float NEG_INF = -1000000.0f;
 
 struct RowStats {
@@ -57,12 +58,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
-__device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_t step, uint32_t row,
-                                                uint32_t col) {
-    const uint4 r = philox4x32_10(make_uint4(col >> 2, row, step, 0u),
+// The uniform of (row, col) is word (col & 3) of the block with counter (col >> 2, row, step, 0): a
+// thread owns four consecutive columns, so one Philox block serves four elements (the first
+// version had consecutive THREADS on consecutive columns and spent 4 blocks per 4 elements: ncu
+// r1j, 77 % of the issue slots, 630 GB/s).
+__device__ __forceinline__ void philox_uniform4(unsigned long long seed, uint32_t step, uint32_t row,
+                                                uint32_t col4, float* uu) {
+    const uint4 r = philox4x32_10(make_uint4(col4, row, step, 0u),
                                   make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-    const uint32_t w = (col & 3) == 0 ? r.x : (col & 3) == 1 ? r.y : (col & 3) == 2 ? r.z : r.w;
-    return static_cast<float>(w >> 8) * (1.0f / 16777216.0f);       // [0, 1)
+    uu[0] = static_cast<float>(r.x >> 8) * (1.0f / 16777216.0f);    // [0, 1)
+    uu[1] = static_cast<float>(r.y >> 8) * (1.0f / 16777216.0f);
+    uu[2] = static_cast<float>(r.z >> 8) * (1.0f / 16777216.0f);
+    uu[3] = static_cast<float>(r.w >> 8) * (1.0f / 16777216.0f);
 }
 
 // MODE 0: ddpm update (race argmax with uniforms)   MODE 1: noise removal (argmax of log p)
@@ -85,33 +92,38 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, const float* 
         return;     // MODE 0/1: copy_flag * x -> x keeps its value
     }
     const float* lr = logits + row * ld;
-    float v[MAX_PER_THREAD];
+    float v[GROUPS * 4];
     float mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < MAX_PER_THREAD; ++k) {
-        const int i = threadIdx.x + k * THREADS;
-        float a = -INFINITY;
-        if (i < V) {
-            a = lr[i];
-            if (i == mask_index) a += NEG_INF;
+    for (int k = 0; k < GROUPS; ++k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * (threadIdx.x + k * THREADS) + e;
+            float a = -INFINITY;
+            if (i < V) {
+                a = lr[i];
+                if (i == mask_index) a += NEG_INF;
+            }
+            v[4 * k + e] = a;
+            mx = fmaxf(mx, a);
         }
-        v[k] = a;
-        mx = fmaxf(mx, a);
     }
     mx = block_max(mx, red);
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < MAX_PER_THREAD; ++k) s += expf(v[k] - mx);      // exp(-inf) = 0 for padding
+    for (int k = 0; k < GROUPS * 4; ++k) s += expf(v[k] - mx);          // exp(-inf) = 0 for padding
     s = block_sum(s, red);
     const float lse = logf(s) + mx;
 
     if constexpr (MODE == 2) {
         float* o = out_logp + row * ld;
 #pragma unroll
-        for (int k = 0; k < MAX_PER_THREAD; ++k) {
-            const int i = threadIdx.x + k * THREADS;
-            if (i < V) o[i] = v[k] - lse;
-        }
+        for (int k = 0; k < GROUPS; ++k)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * (threadIdx.x + k * THREADS) + e;
+                if (i < V) o[i] = v[4 * k + e] - lse;
+            }
         return;
     }
 
@@ -119,20 +131,30 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, const float* 
     int best_i = 0x7fffffff;
     const float dmc = mc_t - mc_s;
 #pragma unroll
-    for (int k = 0; k < MAX_PER_THREAD; ++k) {
-        const int i = threadIdx.x + k * THREADS;
-        if (i < V) {
-            float score;
+    for (int k = 0; k < GROUPS; ++k) {
+        const int i0 = 4 * (threadIdx.x + k * THREADS);
+        if (i0 < V) {
+            float uu[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr (MODE == 0) {
-                float q = expf(v[k] - lse) * dmc;
-                if (i == mask_index) q = mc_s;
-                const float uu = u ? u[row * ld + i] : philox_uniform(seed, step, row, i);
-                const float g = 1e-10f - logf(uu + 1e-10f);
-                score = q / g;
-            } else {
-                score = v[k] - lse;
+                if (u == nullptr) philox_uniform4(seed, step, row, i0 >> 2, uu);
             }
-            if (score > best) { best = score; best_i = i; }      // ascending i: first max wins
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = i0 + e;
+                if (i < V) {
+                    float score;
+                    if constexpr (MODE == 0) {
+                        float q = expf(v[4 * k + e] - lse) * dmc;
+                        if (i == mask_index) q = mc_s;
+                        const float ur = u ? u[row * ld + i] : uu[e];
+                        const float g = 1e-10f - logf(ur + 1e-10f);
+                        score = q / g;
+                    } else {
+                        score = v[4 * k + e] - lse;
+                    }
+                    if (score > best) { best = score; best_i = i; }      // ascending i: first max wins
+                }
+            }
         }
     }
     // (max score, min index) reduction
