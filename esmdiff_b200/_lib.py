@@ -116,7 +116,8 @@ def lib() -> C.CDLL:
                 raise EsmdiffError(
                     f"{LIB_PATH} is missing and could not be built ({e}); esmdiff_b200 has no "
                     "fallback path -- run __graft_entry__.build() where nvcc is available") from e
-    L = C.CDLL(str(LIB_PATH))
+    # ESMDIFF_LIB: load another build of the same library (kernel experiments, tools/)
+    L = C.CDLL(os.environ.get("ESMDIFF_LIB", str(LIB_PATH)))
     for name, (res, args) in _SIGS.items():
         fn = getattr(L, name)          # AttributeError if the .so does not export it
         fn.restype, fn.argtypes = res, args

@@ -96,7 +96,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // One 128-byte line (32 fp32) of a residual-stream row <-> registers, as four 256-bit accesses.
+#ifndef RESID_DEBUG_SKIP
+#define RESID_DEBUG_SKIP 0      // experiments only: 1 = no x loads, 2 = no x/xb stores, 3 = neither
+#endif
 __device__ __forceinline__ void ld_row128(float* r, const float* g) {
+    if (RESID_DEBUG_SKIP & 1) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         asm volatile("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -106,6 +110,7 @@ __device__ __forceinline__ void ld_row128(float* r, const float* g) {
                      : "memory");
 }
 __device__ __forceinline__ void st_row128(float* g, const float* r) {
+    if (RESID_DEBUG_SKIP & 2) return;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         asm volatile("st.global.v8.f32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
@@ -114,8 +119,46 @@ __device__ __forceinline__ void st_row128(float* g, const float* r) {
                      : "memory");
 }
 
+// 4 consecutive fp32 / bf16 of one row.
+__device__ __forceinline__ void ld_quad(float* r, const float* g) {
+    if (RESID_DEBUG_SKIP & 1) return;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(g) : "memory");
+}
+__device__ __forceinline__ void st_quad(float* g, const float* r) {
+    if (RESID_DEBUG_SKIP & 2) return;
+    asm volatile("st.global.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]), "l"(g) : "memory");
+}
+__device__ __forceinline__ void st_quad_bf16(__nv_bfloat16* g, const float* r) {
+    if (RESID_DEBUG_SKIP & 2) return;
+    asm volatile("st.global.v2.b32 [%2], {%0, %1};" ::"r"(pack_bf16x2(r[0], r[1])), "r"(pack_bf16x2(r[2], r[3])), "l"(g) : "memory");
+}
+// 8 x 8 transpose of 4-float blocks inside every group of 8 lanes: in, lane k holds block i in
+// a[4 i .. 4 i + 3] (its own row, column quad i); out, lane i holds block k (row k of the group,
+// column quad i) in the same slots.  Three butterfly stages of 16 shuffles, registers only (the
+// same transpose through 4 KiB of swizzled shared memory per warp -- 16 LDS/STS.128 instead of
+// ~190 instructions -- measured slower in situ: the main loop competes for shared-memory bandwidth).
+__device__ __forceinline__ void transpose_quads8(float* a, int lane) {
+#pragma unroll
+    for (int b = 4; b >= 1; b >>= 1) {
+        const bool up = lane & b;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j & b) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float send = up ? a[4 * j + e] : a[4 * (j | b) + e];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, b);
+                if (up) a[4 * j + e] = recv;
+                else a[4 * (j | b) + e] = recv;
+            }
+        }
+    }
+}
+
 // 32 bf16 of one row (64 bytes) as two 256-bit stores.
 __device__ __forceinline__ void st_row64(__nv_bfloat16* g, const uint32_t* r) {
+    if (RESID_DEBUG_SKIP & 2) return;
 #pragma unroll
     for (int i = 0; i < 2; ++i)
         asm volatile("st.global.v8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
@@ -200,7 +243,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if constexpr (C::BOXES == 1 && EPI != EPI_BIAS_GELU_F32 && EPI != EPI_BIAS_F32) tma_prefetch_desc(&tmC);
+        if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_STORE_BF16_LN || EPI == EPI_SWIGLU_BF16_LN) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -437,71 +480,110 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     bulk_commit_group();
                 }
             } else if constexpr (RESID) {
-                // residual stream update x = x + acc / scale, entirely in registers: thread = row,
-                // one 32-column chunk of a row is one 128-byte line, moved as four 256-bit
-                // loads/stores.  Nothing touches shared memory here, which matters because the main
-                // loop already runs at the shared-memory bandwidth limit (TMA fill + UMMA operand
-                // reads ~ 125 B/clk/SM): the earlier TMA-staged form (load box -> add in smem ->
-                // store box, 512 KiB of extra smem traffic per tile) held out_proj to 0.74-0.93
-                // PFLOP/s.  Loads run two chunks ahead in two register sets; the first two chunks of
-                // the NEXT tile are requested while this tile drains, so they land during its main
-                // loop.  acc / scale is evaluated as acc * (1 / scale): <= 1 ulp(fp32) from the
-                // reference's division, far below the bf16 rounding of the GEMM operands.
+                // residual stream update x = x + acc / scale: x moves global <-> registers directly
+                // (a TMA-staged form, 512 KiB of shared-memory traffic per tile on top of a main loop
+                // already near the shared-memory bandwidth limit, held out_proj to 0.74-0.93 PFLOP/s).
+                // Access pattern: a 32x32b TMEM load puts a token ROW in each thread, and the first
+                // version read/wrote x that way (a 32-byte sector per lane = 32 L1 wavefronts per
+                // instruction, 10 240 per tile).  tools/l2test.py with loads or stores compiled out
+                // shows each alone is free but together they exceed the 12.3k-clk main loop of a
+                // K = 1536 tile (out_proj 123-145 us vs 80 us) independent of L2 residency: the LSU
+                // pipe, at ~2 clk per wavefront.  So the accumulator chunk is transposed in 8 x 8
+                // blocks of 4 floats across each group of 8 lanes (48 shuffles): afterwards lane i of
+                // a group holds columns [4 i, 4 i + 4) of all 8 rows of the group, and every 128-bit
+                // access has 8 lanes on one 128-byte line: 4x fewer wavefronts, same instruction
+                // count.  Loads run two chunks ahead in two register sets; the first two chunks of
+                // the NEXT tile are requested while this tile drains.  acc / scale is evaluated as
+                // acc * (1 / scale): <= 1 ulp(fp32) from the reference's division.
                 constexpr int NCH = (BN / 2) / 32;
                 static_assert(NCH == 4, "two alternating register sets need an even chunk count");
                 float* xg = reinterpret_cast<float*>(p.out);
                 const float inv = 1.0f / p.scale;
-                auto chunk_ptr = [&](int t, int c) {
-                    const long long row = static_cast<long long>(t / p.n_tiles) * BM + rank * BM_CTA + q * 32 + lane;
-                    return xg + row * p.ldo + (t % p.n_tiles) * BN + half * (BN / 2) + c * 32;
+                const int grp = lane >> 3, qd = lane & 7;                  // rows 8 grp .. 8 grp + 7, column quad qd
+                // first of my 8 rows and my 4 columns in chunk c of tile t
+                auto quad_ptr = [&](int t, int c) {
+                    const long long row = static_cast<long long>(t / p.n_tiles) * BM + rank * BM_CTA + q * 32 + grp * 8;
+                    return xg + row * p.ldo + (t % p.n_tiles) * BN + half * (BN / 2) + c * 32 + qd * 4;
                 };
-                auto row_ok = [&](int t) { return (t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA + q * 32 + lane < p.M; };
-                const bool ok = row_ok(tile);
-                if (tile == cluster_id && ok) {         // first tile of this CTA pair: nothing prefetched yet
-                    ld_row128(xres, chunk_ptr(tile, 0));
-                    ld_row128(xres + 32, chunk_ptr(tile, 1));
+                auto rows_left = [&](int t) { return p.M - ((t / p.n_tiles) * BM + static_cast<int>(rank) * BM_CTA + q * 32 + grp * 8); };
+                auto ld_chunk = [&](float* xr, int t, int c) {
+                    const float* src = quad_ptr(t, c);
+                    const int nr = rows_left(t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k < nr) ld_quad(xr + 4 * k, src + static_cast<long long>(k) * p.ldo);
+                };
+                const int nr = rows_left(tile);
+                if (tile == cluster_id) {               // first tile of this CTA pair: nothing prefetched yet
+                    ld_chunk(xres, tile, 0);
+                    ld_chunk(xres + 32, tile, 1);
                 }
                 const int nt = tile + num_clusters;
-                const bool ok_next = nt < num_tiles && row_ok(nt);
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
-                // EPI_RESID_F32_LN: statistics of this thread's 128 columns of the updated row,
-                // shifted by the first element so that sum((x-k)^2) - sum(x-k)^2/n does not cancel
-                float st_shift = 0.f, st_s = 0.f, st_q = 0.f;
+                // EPI_RESID_F32_LN: (sum, sum of squares) of my 4 columns of each of the 8 rows, over
+                // the warp's four chunks.  Plain sums over a 128-column span: M2 = q - s^2/128 loses
+                // ~1e-7 (1 + (span mean / span std)^2) relative, harmless for a residual stream whose
+                // span means are of the order of its spread; the spans are then combined exactly
+                // (Chan) by the consumer.
+                float st_s[8], st_q[8];
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    float* xr = (c & 1) ? xres + 32 : xres;
+                for (int k = 0; k < 8; ++k) { st_s[k] = 0.f; st_q[k] = 0.f; }
+#pragma unroll 1
+                for (int c2 = 0; c2 < NCH; c2 += 2)
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = c2 + cc;
+                    float* xr = cc ? xres + 32 : xres;
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
+                    float* a = reinterpret_cast<float*>(v);
+                    transpose_quads8(a, lane);
+                    float* dst = quad_ptr(tile, c);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) xr[j] = fmaf(__uint_as_float(v[j]), inv, xr[j]);
-                    if (ok) st_row128(chunk_ptr(tile, c), xr);
+                    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) xr[4 * k + e] = fmaf(a[4 * k + e], inv, xr[4 * k + e]);
+                        if (k < nr) st_quad(dst + static_cast<long long>(k) * p.ldo, xr + 4 * k);
+                    }
                     if constexpr (EPI == EPI_RESID_F32_LN) {
-                        if (c == 0) st_shift = xr[0];
-                        uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float d = xr[j] - st_shift;
-                            st_s += d;
-                            st_q = fmaf(d, d, st_q);
+                        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                st_s[k] += xr[4 * k + e];
+                                st_q[k] = fmaf(xr[4 * k + e], xr[4 * k + e], st_q[k]);
+                            }
+                            if (k < nr) st_quad_bf16(p.xb_out + (dst - xg) + static_cast<long long>(k) * p.ldo, xr + 4 * k);
                         }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(xr[2 * j], xr[2 * j + 1]);
-                        if (ok) st_row64(p.xb_out + (chunk_ptr(tile, c) - xg), pk);
                     }
-                    if (c + 2 < NCH) {
-                        if (ok) ld_row128(xr, chunk_ptr(tile, c + 2));
-                    } else if (ok_next) {
-                        ld_row128(xr, chunk_ptr(nt, c + 2 - NCH));
-                    }
+                    if (c + 2 < NCH) ld_chunk(xr, tile, c + 2);
+                    else if (nt < num_tiles) ld_chunk(xr, nt, c + 2 - NCH);
                 }
                 if constexpr (EPI == EPI_RESID_F32_LN) {
-                    if (ok) {
-                        const long long row = static_cast<long long>(row_base + lane);
-                        const float sm = st_s * (1.0f / LN_SPAN);
-                        p.stats_out[row * (p.N / LN_SPAN) + nb * (BN / LN_SPAN) + half] =
-                            make_float2(st_shift + sm, st_q - st_s * sm);
+                    // add the 8 column quads of each row: 8 items over 8 lanes -> lane qd ends with row qd
+#pragma unroll
+                    for (int b = 4; b >= 1; b >>= 1) {
+                        const bool up = lane & b;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j & b) continue;
+                            const float ss = up ? st_s[j] : st_s[j | b], sq = up ? st_q[j] : st_q[j | b];
+                            const float rs = __shfl_xor_sync(0xffffffffu, ss, b), rq = __shfl_xor_sync(0xffffffffu, sq, b);
+                            if (up) { st_s[j | b] += rs; st_q[j | b] += rq; }
+                            else { st_s[j] += rs; st_q[j] += rq; }
+                        }
+                    }
+                    // lane qd now holds the totals of row qd of its group in slot qd
+                    float my_s = st_s[0], my_q = st_q[0];
+#pragma unroll
+                    for (int k = 1; k < 8; ++k)
+                        if (qd == k) { my_s = st_s[k]; my_q = st_q[k]; }
+                    if (qd < nr) {
+                        const long long row = static_cast<long long>(row_base + grp * 8 + qd);
+                        const float sm = my_s * (1.0f / LN_SPAN);
+                        p.stats_out[row * (p.N / LN_SPAN) + nb * (BN / LN_SPAN) + half] = make_float2(sm, my_q - my_s * sm);
                     }
                 }
             } else {
@@ -542,7 +624,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[acc]), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (C::BOXES == 1 && EPI != EPI_BIAS_GELU_F32 && EPI != EPI_BIAS_F32) {
+        if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_STORE_BF16_LN || EPI == EPI_SWIGLU_BF16_LN) {
             if (lane == 0) bulk_wait_group<0>();                  // stores complete before exit
         }
     }
