@@ -88,6 +88,21 @@ struct esmdiff_ctx {
 
     std::map<std::tuple<const void*, uint64_t, uint64_t, uint32_t, uint32_t>, CUtensorMap> tmaps;
 
+    // CUDA graphs of one forward for small batches (esmdiff_ddpm_sample): at B*T of a few hundred
+    // rows the ~290 kernels of a forward are launch-latency bound (sweep: 24 us per launch against
+    // 5-10 us of work).  Keyed by the shape and the token pointers the captured kernels read.
+    int graph_mode = -1;                       // ESMDIFF_GRAPH: 0 never, 1 always, -1 when B*T <= graph_max_rows
+    int64_t graph_max_rows = 8192;
+    cudaStream_t gstream = nullptr;            // capture is illegal on the legacy default stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    struct GraphRec { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; bool warmed = false; };
+    std::map<std::tuple<int, int, const void*, const void*>, GraphRec> graphs;
+    void drop_graphs() {
+        for (auto& kv : graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        graphs.clear();
+    }
+
     // optional per-launch device timing (esmdiff_profile_*): CUDA events on the launching stream
     struct ProfRec { int kind; double work; cudaEvent_t a, b; };
     bool prof = false;
@@ -413,6 +428,7 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
                 if (q == o) q = nullptr;
         }
     c->tmaps.clear();
+    c->drop_graphs();                          // captured kernels point into the old workspace
     const int64_t D = c->cfg.d_model, F = c->cfg.ffn_hidden, V = c->cfg.n_structure_heads;
     c->x = nullptr; c->headh = nullptr; c->logits_ws = nullptr;
     c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr; c->stats = nullptr;
@@ -493,6 +509,60 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
     if (launch_gemm(c, gemm::EPI_BIAS_GELU_F32, c->xn, c->h0_w, M, D, D, c->headh, D, c->h0_b, 1.f, st)) return 1;
     if (launch_layernorm(c, c->headh, c->h2_w, c->h2_b, c->xn, M, D, st)) return 1;
     if (launch_gemm(c, gemm::EPI_BIAS_F32, c->xn, c->h3_w, M, V, D, logits, V, c->h3_b, 1.f, st)) return 1;
+    return 0;
+}
+
+// One forward of the sampling loop, replayed from a CUDA graph when the batch is small enough to be
+// launch bound.  The first call for a key runs eagerly (allocations, function attributes, TMA
+// descriptors), the second captures, later ones replay.  Falls back to eager launches whenever
+// capture is not possible (profiling on, capture failure).
+static int forward_step(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T, float* logits,
+                        cudaStream_t st) {
+    const int64_t M = (int64_t)B * T;
+    const bool want = !c->prof && (c->graph_mode == 1 || (c->graph_mode == -1 && M <= c->graph_max_rows));
+    if (!want) return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
+    auto key = std::make_tuple(B, T, (const void*)seq, (const void*)xt);
+    if (c->graphs.size() > 64 && !c->graphs.count(key)) c->drop_graphs();     // callers that never reuse buffers
+    esmdiff_ctx::GraphRec& g = c->graphs[key];
+    if (logits != c->logits_ws) return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
+    if (!g.exec) {
+        if (!g.warmed) {
+            g.warmed = true;
+            return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
+        }
+        if (!c->gstream) {
+            CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        }
+        const int64_t l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeThreadLocal));
+        const int rc = forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, c->gstream);
+        const cudaError_t e = cudaStreamEndCapture(c->gstream, &graph);
+        g.kernels = c->launches - l0;
+        c->launches = l0;                                  // nothing ran yet
+        if (rc != 0 || e != cudaSuccess || graph == nullptr) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            c->graph_mode = 0;                             // do not try again
+            return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            g.exec = nullptr;
+            cudaGetLastError();
+            c->graph_mode = 0;
+            return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
+        }
+    }
+    CK(cudaEventRecord(c->ev_fork, st));
+    CK(cudaStreamWaitEvent(c->gstream, c->ev_fork, 0));
+    CK(cudaGraphLaunch(g.exec, c->gstream));
+    CK(cudaEventRecord(c->ev_join, c->gstream));
+    CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    c->launches += g.kernels;
     return 0;
 }
 
@@ -666,6 +736,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_ATTN"))
         c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "tiles") == 0 ? 2 : strcmp(e, "qtmem") == 0 ? 3 : 0;
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
+    if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -692,6 +763,10 @@ int esmdiff_destroy(esmdiff_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    c->drop_graphs();
+    if (c->gstream) cudaStreamDestroy(c->gstream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (void* p : c->owned)
         if (p) cudaFree(p);
     for (LayerW& w : c->layers) {
@@ -899,13 +974,13 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
     }
     for (int i = 0; i < steps; ++i) {
         if (launch_time_embed(c, sigma[i], c->cond, st)) return 1;
-        if (forward_impl(c, seq, out, B, T, c->cond, 0, c->logits_ws, nullptr, st)) return 1;
+        if (forward_step(c, seq, out, B, T, c->logits_ws, st)) return 1;
         if (launch_sampler<0>(c, c->logits_ws, nullptr, out, nullptr, M, mc_t[i], mc_s[i], seed, (uint32_t)i, st))
             return 1;
     }
     if (noise_removal) {
         if (launch_time_embed(c, sigma[steps], c->cond, st)) return 1;
-        if (forward_impl(c, seq, out, B, T, c->cond, 0, c->logits_ws, nullptr, st)) return 1;
+        if (forward_step(c, seq, out, B, T, c->logits_ws, st)) return 1;
         if (launch_sampler<1>(c, c->logits_ws, nullptr, out, nullptr, M, 0.f, 0.f, 0, 0, st)) return 1;
     }
     return 0;
