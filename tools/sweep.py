@@ -3,7 +3,7 @@
 
     gpurun -- python tools/sweep.py > profiles/<round>_sweep.md     (one GPU, ~3 min)
 
-Per cell: structure-tokens/s (device-resident inputs, CUDA events, one warm run per shape class),
+Per cell: structure-tokens/s (device-resident inputs, CUDA events, after a 2-step warm run of the cell),
 whole-job TFLOP/s on the algorithmic FLOPs of SURVEY.md 8(d) and its fraction of the measured
 sustained bf16 peak, share of the time in the tcgen05 GEMMs / attention, HBM GB/s of the sampling
 kernel.  The reference's CPU path beside it is bench.py's cpu_baseline (one number per box)."""
@@ -48,8 +48,12 @@ def main():
                         for i, b in enumerate(chunks)]
                 return torch.cat(outs)
 
-            if N in (1, 8):
-                job(1)                                    # warm (allocations, tensor maps)
+            # warm every cell with a 2-step run: the first call at a larger B*T re-allocates the library
+            # workspace (cudaFree + cudaMalloc of GBs: seconds of host time), builds TMA descriptors and,
+            # for small batches, captures the CUDA graph -- one-time costs, not throughput
+            warm = eng.schedule(2)
+            for i, b in enumerate(chunks):
+                eng.ddpm_sample(seq[None].expand(b, T).contiguous(), None, 2, *warm, seed=i)
             torch.cuda.synchronize()
             eng.profile(True)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
