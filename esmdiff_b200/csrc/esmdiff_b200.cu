@@ -16,7 +16,6 @@
 #include <vector>
 
 #include "attention.cuh"
-#include "attention_qtmem.cuh"
 #include "attention_resident.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
@@ -59,8 +58,7 @@ struct esmdiff_ctx {
     std::string err;
     int64_t launches = 0;
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
-                               // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles),
-                               // 3 = experimental Q-in-TMEM / 8-softmax-warp kernel (qtmem; slower)
+                               // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
     EncodeTiledFn encode = nullptr;
 
@@ -349,32 +347,6 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     const int smem = attn2::smem_bytes(nkv, tail_cols);
     if (c->attn_variant == 1 || nkv > attn2::MAX_KV_TILES || smem > 227 * 1024)
         return launch_attention_streaming(c, qkv, out, B, T, H, st);
-    if (c->attn_variant == 3) {
-        const int D = H * attn4::DH;
-        const int64_t M = (int64_t)B * T;
-        CUtensorMap tkv, tkvt;
-        if (get_tmap(c, qkv, M, 3 * D, 3 * D, attn4::BKV, &tkv)) return 1;
-        if (get_tmap(c, qkv, M, 3 * D, 3 * D, tail_cols, &tkvt)) return 1;
-        attn4::Params p;
-        p.B = B; p.T = T; p.H = H;
-        p.nq = (T + attn4::BQ - 1) / attn4::BQ;
-        p.nkv = nkv;
-        p.tail_cols = tail_cols;
-        p.qkv = qkv;
-        p.ctx = out;
-        p.scale_log2 = 0.125f * 1.4426950408889634f;
-        const int smem4 = attn4::smem_bytes(nkv, tail_cols);
-        static int attr_smem4 = 0;
-        if (smem4 > attr_smem4) {
-            CK(cudaFuncSetAttribute(attn4::attention_qtmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-            attr_smem4 = smem4;
-        }
-        ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn4::DH, st);
-        attn4::attention_qtmem_kernel<<<B * H, attn4::THREADS, smem4, st>>>(tkv, tkvt, p);
-        c->launches++;
-        CK(cudaGetLastError());
-        return 0;
-    }
     const int D = H * attn2::DH;
     const int64_t M = (int64_t)B * T;
     CUtensorMap tq, tkv, tkvt;
@@ -734,7 +706,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->layers.resize(cfg->n_layers);
     if (const char* e = getenv("ESMDIFF_ATTN"))
-        c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "tiles") == 0 ? 2 : strcmp(e, "qtmem") == 0 ? 3 : 0;
+        c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "tiles") == 0 ? 2 : 0;
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;

@@ -1,3 +1,6 @@
+// EXPERIMENT, not part of the library (see DESIGN.md "What bounds attention here"): correct but
+// slower than attention_resident.cuh (214 vs 156 us at B = 100, T = 258).  Built only by
+// tools/attn_trace.cu.
 // Non-causal multi-head attention, d_head = 64, for the sequence lengths the sampling path is quoted
 // on (T = L + 2 <= 766).  Replaces F.scaled_dot_product_attention on the reference path
 // (esm MultiHeadAttention.forward with seq_id None).
@@ -29,7 +32,7 @@
 // Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64; q,k already LayerNormed + RoPE'd)
 // Output ctx : bf16 [M, D]
 #pragma once
-#include "ptx.cuh"
+#include "../../esmdiff_b200/csrc/ptx.cuh"
 
 namespace esmdiff {
 namespace attn4 {
