@@ -192,6 +192,8 @@ def workload_config(chunks=None, n_gpus=1, rng="philox"):
 # GPU arm
 # ---------------------------------------------------------------------------------------------
 def gpu_bench(args):
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     from esmdiff_b200 import distributed as D
     from esmdiff_b200.engine import Dims, Engine
     from esmdiff_b200.model import MaskedDiffusionLanguageModeling
