@@ -177,6 +177,27 @@ def test_gemm_layernorm_folded_epilogues(engine, M, D, F_h):
     assert rel_fro(qkv, ln @ wq.T) < 1.5 * rel_fro(qkv2, ln @ wq.T) + 1e-4
 
 
+def test_residual_epilogue_statistics_with_large_row_offset(engine):
+    """The residual epilogue accumulates plain (sum, sum of squares) per 128-column span; the claimed
+    loss is ~1e-7 (1 + (mean/std)^2) relative.  Pin it at mean/std = 50 (far beyond a LayerNorm
+    input): variance within 1e-3, i.e. rstd within 5e-4, below the bf16 rounding of the operands."""
+    g = torch.Generator(device=DEV).manual_seed(12)
+    M, D = 777, 1536
+    a = torch.zeros(M, D, device=DEV).bfloat16()                 # acc = 0: the statistics are those of x0
+    wo = torch.zeros(D, D, device=DEV).bfloat16()
+    x0 = 50.0 + torch.randn(M, D, device=DEV, generator=g)
+    x = x0.clone()
+    xb = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(M, D // 128, 2, device=DEV)
+    engine.op_gemm_ln(6, a, wo, x, scale=1.0, stats_out=stats, xb_out=xb)
+    engine.synchronize()
+    assert torch.equal(x, x0)
+    mean, var = _combine_stats(stats, D)
+    ref_var = x0.double().var(-1, unbiased=False)
+    assert float((mean - x0.double().mean(-1)).abs().max()) < 1e-4
+    assert float(((var - ref_var).abs() / ref_var).max()) < 1e-3
+
+
 # ---------------------------------------------------------------------------------------------
 # row kernels
 # ---------------------------------------------------------------------------------------------
