@@ -92,6 +92,10 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
         cs[4] = bq.x; cs[5] = bq.y; cs[6] = bq.z; cs[7] = bq.w;
         sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w;
         sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
+        if (!upper) {                            // lower half: x1*c - x2*s ; upper half: x2*c + x1*s
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sn[e] = -sn[e];
+        }
     }
     // q, then k.  The values stay PACKED (bf16 pairs) in registers and are unpacked again in each of
     // the three passes (one shift or mask per element): keeping fp32 copies of both rows cost 119
@@ -129,6 +133,7 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
                 }
             }
         const float rstd = rsqrtf(warp_sum(q) / D + eps);
+        const float nmean = -mean;
 #pragma unroll
         for (int i = 0; i < MAXC; ++i)
             if (i < nc) {
@@ -139,14 +144,15 @@ qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restric
                 float n[8], out[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    n[2 * e] = (lo(r4[e]) - mean) * rstd * ww[2 * e];
-                    n[2 * e + 1] = (hi(r4[e]) - mean) * rstd * ww[2 * e + 1];
+                    const float a0 = rstd * ww[2 * e], a1 = rstd * ww[2 * e + 1];
+                    n[2 * e] = fmaf(lo(r4[e]), a0, nmean * a0);          // (x - mean) * rstd * w
+                    n[2 * e + 1] = fmaf(hi(r4[e]), a1, nmean * a1);
                 }
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float partner = __shfl_xor_sync(0xffffffffu, n[e], 4);
-                    // lower half: x1*c - x2*s ; upper half: x2*c + x1*s
-                    out[e] = upper ? (n[e] * cs[e] + partner * sn[e]) : (n[e] * cs[e] - partner * sn[e]);
+                    // lower half: x1*c - x2*s ; upper half: x2*c + x1*s   (sn carries the sign)
+                    out[e] = fmaf(partner, sn[e], n[e] * cs[e]);
                 }
                 *reinterpret_cast<uint4*>(base + i * 256 + lane * 8) =
                     make_uint4(pack_bf16x2(out[0], out[1]), pack_bf16x2(out[2], out[3]),
