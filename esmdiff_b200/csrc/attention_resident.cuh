@@ -160,7 +160,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint64_t* q_full = bars;                              // [2]
     uint64_t* q_empty = bars + 2;                         // [2]
     uint64_t* s_full = bars + 4;                          // [2]  MMA -> softmax
-    uint64_t* p_full = bars + 6;                          // [2]  softmax (128 threads) -> MMA
+    uint64_t* p_full = bars + 6;                          // [2]  softmax warps (4 arrivals) -> MMA
     uint64_t* pv_done = bars + 8;                         // 1    P V of step nsteps-2 retired (no S follows it)
     uint64_t* o_free = bars + 9;                          // 1    completes once per query tile
     uint64_t* o_full = bars + 10;                         // 1    last PV of a query tile retired
@@ -186,10 +186,10 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             mbar_init(&q_full[s], 1);
             mbar_init(&q_empty[s], 1);
             mbar_init(&s_full[s], 1);
-            mbar_init(&p_full[s], 128);
+            mbar_init(&p_full[s], 4);              // one arrival per softmax warp
         }
         mbar_init(pv_done, 1);
-        mbar_init(o_free, 128);
+        mbar_init(o_free, 4);
         mbar_init(o_full, 1);
         for (int j = 0; j < nkv; ++j) {
             mbar_init(&k_full[j], 1);
@@ -338,7 +338,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                 }
             }
             tcgen05_fence_before();
-            mbar_arrive(o_free);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_free);
         };
 
         float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
@@ -425,8 +426,11 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                     l_run += rs0 + rs1;
                     tmem_st_wait();
                 }
+                // one arrival per warp: 128 per-thread arrivals are 128 serialised shared-memory atomics
+                // on the critical path of every step
                 tcgen05_fence_before();
-                mbar_arrive(&p_full[i & 1]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&p_full[i & 1]);
                 if (j == 0 && qt > 0) epilogue(qt - 1, l_prev);   // deferred: overlaps this tile's first MMAs
             }
         }
