@@ -98,6 +98,12 @@ _SIGS = {
     "esmdiff_op_qk_norm_rope": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "esmdiff_op_attention": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "esmdiff_op_convert_bf16": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
+    "esmdiff_set_time_conditioning": (C.c_int, [_P, C.c_int]),
+    "esmdiff_op_fold_layernorm_centered": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64,
+                                                     C.c_int64, C.c_int64, _P]),
+    "esmdiff_op_gemm_qkv_rope": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P,
+                                           _P, _P, C.c_int, C.c_int, _P]),
+    "esmdiff_op_attention_ln": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
 }
 EXPORTED = tuple(_SIGS)
 _lib = None
@@ -121,7 +127,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in _SIGS.items():
         fn = getattr(L, name)          # AttributeError if the .so does not export it
         fn.restype, fn.argtypes = res, args
-    if L.esmdiff_abi_version() != 1:
+    if L.esmdiff_abi_version() != 2:
         raise EsmdiffError("ABI version mismatch between _lib.py and libesmdiff_b200.so")
     _lib = L
     return L

@@ -11,7 +11,11 @@
 //              registers and rescaled there (no TMEM read-modify-write).
 // Two CTAs fit per SM (about 81 KiB smem, 256 TMEM columns each), so one CTA's softmax overlaps
 // the other's MMAs.
-// Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64; q,k already LayerNormed + RoPE'd)
+// Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64).  With qk_sumsq == null q, k are
+//   already LayerNormed + RoPE'd; otherwise they are the un-normalised q', k' of gemm.cuh's
+//   EPI_QKV_ROPE_LN and the per-row factors 1/std are applied here in fp32: rstd_q[i] in the scale
+//   of query row i, rstd_k[j] per score column from a shared-memory table (K tiles are streamed
+//   through a ring here, so they are not rescaled in place as attention_resident.cuh does).
 // Output ctx : bf16 [M, D]
 #pragma once
 #include "ptx.cuh"
@@ -35,7 +39,11 @@ struct Params {
     int q_tiles;                // ceil(T / BQ)
     __nv_bfloat16* ctx;         // [B*T, H*64]
     float scale_log2;           // (1/sqrt(64)) * log2(e)
+    const float* qk_sumsq;      // [B*T][2 * nspan] (q spans then k spans) or null
+    int nspan;                  // D / 128
+    float ln_eps;
 };
+__host__ inline int smem_bytes(int T) { return SMEM_BYTES + ((T + BKV - 1) / BKV) * BKV * 4; }
 
 __global__ void __launch_bounds__(THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128 rows][64 cols]
@@ -59,6 +67,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
     uint64_t* p_full = bars + 17;             // 1
     uint64_t* o_full = bars + 18;             // 1
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    float* rk_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [nkv * 64] rstd_k per key
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -71,7 +80,20 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
     const int row0 = b * p.T;                   // first token row of this sample
     const int q0 = qt * BQ;                     // first query position of this tile
     const int nkv = (p.T + BKV - 1) / BKV;
+    const bool fused_ln = p.qk_sumsq != nullptr;
 
+    if (fused_ln) {
+        for (int t = threadIdx.x; t < nkv * BKV; t += THREADS) {
+            float rk = 0.f;
+            if (t < p.T) {
+                const float* part = p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan + p.nspan;
+                float ss = 0.f;
+                for (int i = 0; i < p.nspan; ++i) ss += __ldg(part + i);
+                rk = rsqrtf(ss / static_cast<float>(p.nspan * 128) + p.ln_eps);
+            }
+            rk_s[t] = rk;
+        }
+    }
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmQKV_q);
         tma_prefetch_desc(&tmQKV_kv);
@@ -167,6 +189,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
         for (int d = 0; d < DH; ++d) acc[d] = 0.f;
         uint8_t* p_row = sP + r * 128;
         const int sw = r & 7;
+        float sc = p.scale_log2;
+        if (fused_ln && q0 + r < p.T) {
+            const float* part = p.qk_sumsq + static_cast<long long>(row0 + q0 + r) * 2 * p.nspan;
+            float ss = 0.f;
+            for (int i = 0; i < p.nspan; ++i) ss += __ldg(part + i);
+            sc *= rsqrtf(ss / static_cast<float>(p.nspan * 128) + p.ln_eps);
+        }
 
         // acc += O_{j}: both are relative to the running max m_run at the time of the call
         auto fold_o = [&](uint32_t parity) {
@@ -199,8 +228,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
             float mx = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float a = __uint_as_float(s0[c]) * p.scale_log2;
-                float bq = __uint_as_float(s1[c]) * p.scale_log2;
+                float a = __uint_as_float(s0[c]) * sc;
+                float bq = __uint_as_float(s1[c]) * sc;
+                if (fused_ln) {
+                    a *= rk_s[j * BKV + c];
+                    bq *= rk_s[j * BKV + c + 32];
+                }
                 a = (c < kv_valid) ? a : -INFINITY;
                 bq = (c + 32 < kv_valid) ? bq : -INFINITY;
                 s0[c] = __float_as_uint(a);

@@ -17,7 +17,15 @@
 //   The last kv tile is only as wide as needed (multiple of 16 columns): T = 258 costs 4 x 64 + 16
 //   columns, not 5 x 64.  Warps whose 32 query rows are all >= T skip the softmax (the 2-row tail
 //   tile of T = 258 keeps one warp busy, not four).
-// Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64; q,k already LayerNormed + RoPE'd)
+// Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64).  Two forms of q, k:
+//   qk_sumsq == null : q, k already LayerNormed + RoPE'd (stand-alone ew::qk_layernorm_rope_kernel)
+//   qk_sumsq != null : q' = rope(gamma_q (q - mean q)), k' likewise, NOT yet divided by their row
+//                      standard deviation, plus the per-row partial sums of (q - mean q)^2 and
+//                      (k - mean k)^2 the QKV GEMM epilogue left (gemm.cuh EPI_QKV_ROPE_LN).  The
+//                      missing factors are per-row scalars: rstd_q[i] goes into the softmax scale of
+//                      query row i (thread = row), rstd_k[j] is multiplied into row j of the
+//                      shared-memory K tile by the two otherwise idle warps before the first S MMA
+//                      reads it (one pass over K per (sample, head): 16 shared-memory accesses per row).
 // Output ctx : bf16 [M, D]
 #pragma once
 #include "ptx.cuh"
@@ -47,7 +55,19 @@ struct Params {
     const __nv_bfloat16* qkv;   // [B*T, 3*H*64] (the leftover warps read their query rows directly)
     __nv_bfloat16* ctx;         // [B*T, H*64]
     float scale_log2;           // (1/sqrt(64)) * log2(e)
+    const float* qk_sumsq;      // [B*T][2 * nspan]: q spans then k spans (gemm.cuh EPI_QKV_ROPE_LN), or null
+    int nspan;                  // D / 128 partial sums per row and operand (<= 12)
+    float ln_eps;               // q_ln / k_ln epsilon
 };
+
+// 1 / sqrt(mean (y - mean y)^2 + eps) of one q or k row from its partial sums of squares.
+__device__ __forceinline__ float row_rstd(const float* part, int nspan, float ln_eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+        if (i < nspan) s += __ldg(part + i);
+    return rsqrtf(s / static_cast<float>(nspan * 128) + ln_eps);
+}
 
 __host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
     return (nkv - 1) * KV_TILE_BYTES + tail_cols * 128;
@@ -65,7 +85,7 @@ __host__ inline int smem_bytes(int nkv, int tail_cols) {
 // registers; P V: lane = two output dims, p broadcast from shared memory.  fp32 throughout.
 __device__ __forceinline__ void leftover_row(const __nv_bfloat16* __restrict__ qrow, __nv_bfloat16* __restrict__ orow,
                                              const uint8_t* sK, const uint8_t* sV, float* pf, int T, float sc,
-                                             uint64_t* k_full, uint64_t* v_full, int nkv, int lane) {
+                                             uint64_t* k_ready, uint64_t* v_full, int nkv, int lane) {
     // q: every lane needs all 64 dims -> 8 x 16-byte loads of the same 128-byte row
     float q[DH];
     {
@@ -81,7 +101,7 @@ __device__ __forceinline__ void leftover_row(const __nv_bfloat16* __restrict__ q
             }
         }
     }
-    for (int j = 0; j < nkv; ++j) mbar_wait(&k_full[j], 0);
+    for (int j = 0; j < nkv; ++j) mbar_wait(&k_ready[j], 0);
     const int nk = (T + 31) >> 5;                      // keys per lane
     float mx = -INFINITY;
     for (int m = 0; m < nk; ++m) {
@@ -166,7 +186,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint64_t* o_full = bars + 10;                         // 1    last PV of a query tile retired
     uint64_t* k_full = bars + 11;                         // [MAX_KV_TILES], single use
     uint64_t* v_full = k_full + MAX_KV_TILES;             // [MAX_KV_TILES], single use
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_full + MAX_KV_TILES);
+    uint64_t* k_scaled = v_full + MAX_KV_TILES;           // [MAX_KV_TILES], single use: K tile multiplied by rstd_k
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_scaled + MAX_KV_TILES);
     float* left_p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [MAX_LEFT][nkv * 64]
 
     const int warp = threadIdx.x >> 5;
@@ -177,6 +198,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     const int row0 = b * p.T;
     const int nq = p.nq, nkv = p.nkv;
     const int nsteps = nq * nkv;
+    const bool fused_ln = p.qk_sumsq != nullptr;
+    uint64_t* k_ready = fused_ln ? k_scaled : k_full;     // what the consumers of K wait for
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -194,6 +217,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         for (int j = 0; j < nkv; ++j) {
             mbar_init(&k_full[j], 1);
             mbar_init(&v_full[j], 1);
+            mbar_init(&k_scaled[j], 2);            // warps 6 and 7
         }
         fence_barrier_init();
     }
@@ -245,7 +269,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         int s_i = 0, s_qt = 0, s_j = 0;                                 // next S = Q K^T to issue
         auto issue_s = [&]() {
             if (s_j == 0) mbar_wait(&q_full[s_qt & 1], (s_qt >> 1) & 1);
-            if (s_qt == 0) mbar_wait(&k_full[s_j], 0);
+            if (s_qt == 0) mbar_wait(&k_ready[s_j], 0);
             tcgen05_fence_after();
             const uint64_t qdesc = desc_q0 + static_cast<uint64_t>((s_qt & 1) * (Q_BYTES >> 4));
             const uint64_t kdesc = desc_k0 + static_cast<uint64_t>(s_j * (KV_TILE_BYTES >> 4));
@@ -299,19 +323,51 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     } else if (warp >= 6) {
         // ===================== trailing query rows past the last full tile =====================
         const int lw = warp - 6;
+        if (fused_ln) {
+            // K rows *= rstd_k (q_ln / k_ln folded into the QKV epilogue, see the header): thread =
+            // row of the 64-row tile; the eight 16-byte chunks of a row are visited in a lane-rotated
+            // order so that the 8 lanes of a quarter warp (rows 128 bytes apart) hit different banks
+            const int tr = threadIdx.x - 6 * 32;
+            for (int j = 0; j < nkv; ++j) {
+                const int t = j * BKV + tr;
+                const bool live = t < p.T;
+                float rk = 0.f;
+                if (live) rk = row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan + p.nspan, p.nspan, p.ln_eps);
+                mbar_wait(&k_full[j], 0);
+                if (live) {
+                    uint8_t* rowp = sK + j * KV_TILE_BYTES + tr * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4* cp = reinterpret_cast<uint4*>(rowp + (((c + lane) & 7) << 4));
+                        const uint4 v = *cp;
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o[e] = pack_bf16x2(__uint_as_float(w[e] << 16) * rk, __uint_as_float(w[e] & 0xffff0000u) * rk);
+                        *cp = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                fence_proxy_async_smem();          // generic-proxy writes -> visible to the UMMA reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&k_scaled[j]);
+            }
+        }
         if (lw < p.n_left) {
             const int t = p.nq * BQ + lw;
+            float sc = p.scale_log2;
+            if (fused_ln) sc *= row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan, p.nspan, p.ln_eps);
             leftover_row(p.qkv + static_cast<long long>(row0 + t) * 3 * D + h * DH,
                          p.ctx + static_cast<long long>(row0 + t) * D + h * DH, sK, sV, left_p + lw * nkv * BKV, p.T,
-                         p.scale_log2, k_full, v_full, nkv, lane);
+                         sc, k_ready, v_full, nkv, lane);
         }
     } else {
         // ===================== softmax / output warps: thread = query row =====================
         const int r = threadIdx.x;                                   // 0..127 == TMEM lane
         const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
         const uint32_t t_o = tmem_base + lane_addr + COL_O;
-        const float sc = p.scale_log2;
-        const float thresh = RESCALE_LOG2 / sc;
+        float sc = p.scale_log2;              // per query row once q_ln's 1/std is folded in (set per query tile)
+        float thresh = RESCALE_LOG2 / sc;
 
         // out[row] = O / l for query tile qt (after its last PV has retired), then free O
         auto epilogue = [&](int qt, float l) {
@@ -352,6 +408,13 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                 if (j == 0) {                 // new query tile: keep the finished tile's row sum for its epilogue
                     l_prev = l_run;
                     l_run = 0.f;
+                    if (fused_ln) {
+                        const int t = qt * BQ + r;
+                        const float rq = t < p.T ? row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan,
+                                                            p.nspan, p.ln_eps) : 1.0f;
+                        sc = p.scale_log2 * rq;
+                        thresh = RESCALE_LOG2 / sc;
+                    }
                 }
                 mbar_wait(&s_full[i & 1], (i >> 1) & 1);
                 tcgen05_fence_after();

@@ -172,6 +172,16 @@ __global__ void rope_table_kernel(const float* __restrict__ inv_freq, float* __r
     sin_t[i] = sinf(f);
 }
 
+// The same table in the layout the QKV GEMM epilogue reads (gemm.cuh EPI_QKV_ROPE_LN): one
+// 256-byte row per token position, cos(t f_i) for i < 32 then sin(t f_i).
+__global__ void rope_rows_kernel(const float* __restrict__ inv_freq, float* __restrict__ rows, int T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * 32) return;
+    const float f = static_cast<float>(i / 32) * inv_freq[i % 32];
+    rows[(i / 32) * 64 + (i % 32)] = cosf(f);
+    rows[(i / 32) * 64 + 32 + (i % 32)] = sinf(f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Input embedding of the ddpm path (esm EncodeInputs with six tracks at their defaults, then
 // CustomizedESM3.forward's "+ auxiliary_embeddings", net.py:445-466):
@@ -286,16 +296,37 @@ time_embed_out_kernel(const float* __restrict__ hidden, const float* __restrict_
     if (lane == 0) cond[j] = s + b2[j];
 }
 
+// Column means over each block of `block_rows` rows: out[b][k] = mean_{r in block b} W[r][k].
+// For the q and k thirds of the QKV weight: q_ln / k_ln subtract the mean over the OUTPUT features
+// of a row, which is linear in the input -- removing these column means from the weight rows makes
+// the GEMM produce q - mean(q) directly (gemm.cuh EPI_QKV_ROPE_LN).
+__global__ void column_mean_kernel(const float* __restrict__ src, float* __restrict__ out, long long block_rows,
+                                   long long cols) {
+    const long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (k >= cols) return;
+    const float* base = src + static_cast<long long>(blockIdx.y) * block_rows * cols + k;
+    float s = 0.f, comp = 0.f;                       // Kahan: 1536 terms of alternating sign
+    for (long long r = 0; r < block_rows; ++r) {
+        const float y = base[r * cols] - comp;
+        const float t = s + y;
+        comp = (t - s) - y;
+        s = t;
+    }
+    out[static_cast<long long>(blockIdx.y) * cols + k] = s / static_cast<float>(block_rows);
+}
+
 // LayerNorm folded into the following Linear (gemm.cuh, *_LN epilogues), one warp per output row n:
-//   dst[n, k]  = bf16(W[src(n), k] * gamma[k])
+//   w[n, k]    = W[src(n), k] - colmean[n / center_block][k]   for n < center_rows (else W[src(n), k])
+//   dst[n, k]  = bf16(w[n, k] * gamma[k])
 //   colsum[n]  = sum_k float(dst[n, k])          (of the ROUNDED weights: it multiplies the row mean)
-//   bias[n]    = sum_k beta[k] * W[src(n), k]    (fp32; beta may be null)
+//   bias[n]    = sum_k beta[k] * w[n, k]         (fp32; beta may be null)
 // src(n) applies the SwiGLU gate/up interleave of convert_rows_bf16_kernel when swiglu_hidden > 0.
 __global__ void __launch_bounds__(256)
 fold_layernorm_weight_kernel(const float* __restrict__ src, const float* __restrict__ gamma,
                              const float* __restrict__ beta, __nv_bfloat16* __restrict__ dst,
                              float* __restrict__ colsum, float* __restrict__ bias, long long rows,
-                             long long cols, int swiglu_hidden) {
+                             long long cols, int swiglu_hidden, const float* __restrict__ colmean = nullptr,
+                             long long center_rows = 0, long long center_block = 1) {
     const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -304,9 +335,11 @@ fold_layernorm_weight_kernel(const float* __restrict__ src, const float* __restr
         const long long blk = r / 256, within = r % 256;
         sr = within < 128 ? blk * 128 + within : swiglu_hidden + blk * 128 + (within - 128);
     }
+    const float* cm = (colmean != nullptr && r < center_rows) ? colmean + (r / center_block) * cols : nullptr;
     float cs = 0.f, bs = 0.f;
     for (long long k = lane; k < cols; k += 32) {
-        const float w = src[sr * cols + k];
+        float w = src[sr * cols + k];
+        if (cm != nullptr) w -= cm[k];
         const __nv_bfloat16 wf = __float2bfloat16_rn(w * gamma[k]);
         dst[r * cols + k] = wf;
         cs += __bfloat162float(wf);

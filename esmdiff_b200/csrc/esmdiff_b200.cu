@@ -43,6 +43,7 @@ struct LayerW {
     // until finalize folds gamma into the bf16 weights; c = colsum(gamma.W), b = beta W^T
     float *wqkv_f32 = nullptr, *w1_f32 = nullptr;
     float *cqkv = nullptr, *bqkv = nullptr, *c1 = nullptr, *b1 = nullptr;
+    float* qk_gamma = nullptr;     // [2 D] q_ln.weight | k_ln.weight (QKV epilogue with q/k-LN + RoPE folded in)
     bool dirty = true;
 };
 
@@ -60,6 +61,11 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
+                               // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: tracked per context, not per process
+    std::set<const void*> smem_attr_set;
+    int attn_resident_smem = 0;
     EncodeTiledFn encode = nullptr;
 
     std::vector<LayerW> layers;
@@ -78,7 +84,8 @@ struct esmdiff_ctx {
     float2* stats = nullptr;                           // [rows][d_model / 128] partial (mean, M2) of x
     bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;
     float *cond = nullptr, *te_hidden = nullptr, *inv_freq = nullptr;
-    float *cos_t = nullptr, *sin_t = nullptr;
+    float *cos_t = nullptr, *sin_t = nullptr, *rope_rows = nullptr, *colmean = nullptr;
+    float* qk_sumsq = nullptr;                         // [rows][2 * d_model / 128] (gemm.cuh EPI_QKV_ROPE_LN)
     int rope_T = 0;
     int* dev_err = nullptr;
     int64_t *x_tok = nullptr, *seq_tok = nullptr;     // staging for the *_host entry point
@@ -193,6 +200,11 @@ struct GemmLN {                // operands of the LayerNorm-folded epilogues (ge
     const float* colsum = nullptr;
     float2* stats_out = nullptr;
     bf16* xb_out = nullptr;
+    // EPI_QKV_ROPE_LN
+    const float* rope = nullptr;
+    const float* qk_gamma = nullptr;
+    float* qk_sumsq = nullptr;
+    int T = 0, n_rope = 0;
 };
 
 static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, int M, int N, int K,
@@ -202,12 +214,16 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     const int max_clusters = c->num_sms / 2;
     const int m_tiles = (M + gemm::BM - 1) / gemm::BM;
     const int BN = 256;
-    const bool is_store = epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_STORE_BF16_LN;
+    const bool is_store = epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_QKV_ROPE_LN;
     const bool is_swiglu = epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_SWIGLU_BF16_LN;
     const bool is_resid = epi == gemm::EPI_RESID_F32 || epi == gemm::EPI_RESID_F32_LN;
-    if ((is_swiglu || is_resid || epi == gemm::EPI_STORE_BF16_LN) && N % BN != 0)
+    if ((is_swiglu || is_resid || epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_QKV_ROPE_LN) && N % BN != 0)
         return c->fail("gemm: SwiGLU / residual / LayerNorm-folded epilogues need N % 256 == 0");
-    if (epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_SWIGLU_BF16_LN) {
+    if (epi == gemm::EPI_QKV_ROPE_LN) {
+        if (!ln.rope || !ln.qk_gamma || !ln.qk_sumsq || ln.T <= 0 || ln.n_rope <= 0 || ln.n_rope % BN != 0 || ln.n_rope > N)
+            return c->fail("gemm: q/k-LayerNorm + RoPE epilogue needs the rotary table, gamma, a statistics buffer, T and n_rope % 256 == 0");
+    }
+    if (epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_SWIGLU_BF16_LN || epi == gemm::EPI_QKV_ROPE_LN) {
         if (!ln.stats_in || !ln.colsum || !bias || K % 256 != 0 || K > 1536)
             return c->fail("gemm: LayerNorm-folded epilogue needs statistics, colsum, bias and K % 256 == 0 <= 1536");
     }
@@ -235,21 +251,22 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
     p.stats_in = ln.stats_in; p.colsum = ln.colsum; p.stats_out = ln.stats_out; p.xb_out = ln.xb_out;
     p.ln_eps = 1e-5f;
+    p.rope = ln.rope; p.qk_gamma = ln.qk_gamma; p.qk_sumsq = ln.qk_sumsq; p.T = ln.T; p.n_rope = ln.n_rope;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
     // profile kinds: the LayerNorm-folded variants are booked under their plain counterparts
-    const int kind = epi == gemm::EPI_STORE_BF16_LN ? gemm::EPI_STORE_BF16
+    const int kind = (epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_QKV_ROPE_LN) ? gemm::EPI_STORE_BF16
                    : epi == gemm::EPI_RESID_F32_LN ? gemm::EPI_RESID_F32
                    : epi == gemm::EPI_SWIGLU_BF16_LN ? gemm::EPI_SWIGLU_BF16 : epi;
     ProfScope prof(c, kind, 2.0 * M * (double)N * K, st);
 #define LAUNCH_GEMM(E, BNV)                                                                    \
     {                                                                                          \
-        static bool attr_set = false;                                                          \
-        if (!attr_set) {                                                                       \
+        const void* fn_ = reinterpret_cast<const void*>(&gemm::gemm_bf16_tn_kernel<E, BNV>);   \
+        if (!c->smem_attr_set.count(fn_)) {                                                    \
             CK(cudaFuncSetAttribute(gemm::gemm_bf16_tn_kernel<E, BNV>,                         \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize,               \
                                     gemm::Cfg<E, BNV>::SMEM_BYTES));                           \
-            attr_set = true;                                                                   \
+            c->smem_attr_set.insert(fn_);                                                      \
         }                                                                                      \
         gemm::gemm_bf16_tn_kernel<E, BNV><<<grid, gemm::THREADS, gemm::Cfg<E, BNV>::SMEM_BYTES, st>>>(ta, tb, tc, p); \
     }
@@ -262,6 +279,7 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
         case gemm::EPI_STORE_BF16_LN: LAUNCH_GEMM(gemm::EPI_STORE_BF16_LN, 256) break;
         case gemm::EPI_RESID_F32_LN: LAUNCH_GEMM(gemm::EPI_RESID_F32_LN, 256) break;
         case gemm::EPI_SWIGLU_BF16_LN: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16_LN, 256) break;
+        case gemm::EPI_QKV_ROPE_LN: LAUNCH_GEMM(gemm::EPI_QKV_ROPE_LN, 256) break;
         default: return c->fail("gemm: unknown epilogue");
     }
 #undef LAUNCH_GEMM
@@ -293,8 +311,11 @@ static int ensure_rope(esmdiff_ctx* c, int T, cudaStream_t st) {
     while (cap < T) cap *= 2;
     if (c->alloc(&c->cos_t, (size_t)cap * 32)) return 1;     // old tables stay owned until destroy
     if (c->alloc(&c->sin_t, (size_t)cap * 32)) return 1;
+    if (c->alloc(&c->rope_rows, (size_t)cap * 64)) return 1;
     ew::rope_table_kernel<<<(cap * 32 + 255) / 256, 256, 0, st>>>(c->inv_freq, c->cos_t, c->sin_t, cap);
-    c->launches++;
+    ew::rope_rows_kernel<<<(cap * 32 + 255) / 256, 256, 0, st>>>(c->inv_freq, c->rope_rows, cap);
+    c->launches += 2;
+    c->drop_graphs();                          // captured kernels point at the old tables
     CK(cudaGetLastError());
     c->rope_T = cap;
     return 0;
@@ -314,7 +335,7 @@ static int launch_qk_norm_rope(esmdiff_ctx* c, bf16* qkv, const float* qw, const
 }
 
 static int launch_attention_streaming(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H,
-                                      cudaStream_t st) {
+                                      const float* qk_sumsq, cudaStream_t st) {
     const int D = H * attn::DH;
     const int64_t M = (int64_t)B * T;
     CUtensorMap tq, tkv;
@@ -325,15 +346,17 @@ static int launch_attention_streaming(esmdiff_ctx* c, const bf16* qkv, bf16* out
     p.q_tiles = (T + attn::BQ - 1) / attn::BQ;
     p.ctx = out;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CK(cudaFuncSetAttribute(attn::attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                attn::SMEM_BYTES));
-        attr_set = true;
+    p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
+    const int smem = attn::smem_bytes(T);
+    if (smem > 227 * 1024) return c->fail("attention: sequence too long for the shared-memory rstd_k table");
+    const void* fn = reinterpret_cast<const void*>(&attn::attention_fwd_kernel);
+    if (!c->smem_attr_set.count(fn)) {
+        CK(cudaFuncSetAttribute(attn::attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        c->smem_attr_set.insert(fn);
     }
     const int grid = B * H * p.q_tiles;
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn::DH, st);
-    attn::attention_fwd_kernel<<<grid, attn::THREADS, attn::SMEM_BYTES, st>>>(tq, tkv, p);
+    attn::attention_fwd_kernel<<<grid, attn::THREADS, smem, st>>>(tq, tkv, p);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -341,12 +364,13 @@ static int launch_attention_streaming(esmdiff_ctx* c, const bf16* qkv, bf16* out
 
 // K/V of one (sample, head) resident in shared memory: every T whose K and V fit beside two query
 // buffers (T <= 766); longer sequences stream K/V tiles (attention.cuh).
-static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H, cudaStream_t st) {
+static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, int T, int H, const float* qk_sumsq,
+                            cudaStream_t st) {
     const int nkv = (T + attn2::BKV - 1) / attn2::BKV;
     const int tail_cols = ((T - (nkv - 1) * attn2::BKV) + 15) / 16 * 16;
     const int smem = attn2::smem_bytes(nkv, tail_cols);
     if (c->attn_variant == 1 || nkv > attn2::MAX_KV_TILES || smem > 227 * 1024)
-        return launch_attention_streaming(c, qkv, out, B, T, H, st);
+        return launch_attention_streaming(c, qkv, out, B, T, H, qk_sumsq, st);
     const int D = H * attn2::DH;
     const int64_t M = (int64_t)B * T;
     CUtensorMap tq, tkv, tkvt;
@@ -366,10 +390,10 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     p.tail_cols = tail_cols;
     p.ctx = out;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
+    p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
+    if (smem > c->attn_resident_smem) {
         CK(cudaFuncSetAttribute(attn2::attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+        c->attn_resident_smem = smem;
     }
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn2::DH, st);
     attn2::attention_resident_kernel<<<B * H, attn2::THREADS, smem, st>>>(tq, tkv, tkvt, p);
@@ -392,7 +416,7 @@ static int launch_time_embed(esmdiff_ctx* c, float sigma, float* cond, cudaStrea
 static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     if (M <= c->ws_rows) return 0;
     // free the previous workspace buffers
-    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf, c->stats};
+    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf, c->stats, c->qk_sumsq};
     for (void* o : olds)
         if (o) {
             cudaFree(o);
@@ -403,8 +427,9 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     c->drop_graphs();                          // captured kernels point into the old workspace
     const int64_t D = c->cfg.d_model, F = c->cfg.ffn_hidden, V = c->cfg.n_structure_heads;
     c->x = nullptr; c->headh = nullptr; c->logits_ws = nullptr;
-    c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr; c->stats = nullptr;
+    c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr; c->stats = nullptr; c->qk_sumsq = nullptr;
     if (c->alloc(&c->stats, M * (D / 128))) return 1;
+    if (c->alloc(&c->qk_sumsq, M * 2 * (D / 128))) return 1;
     if (c->alloc(&c->x, M * D)) return 1;
     if (c->alloc(&c->headh, M * D)) return 1;
     if (c->alloc(&c->logits_ws, M * V)) return 1;
@@ -429,6 +454,7 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
     const int M = (int)M64;
     const int D = c->cfg.d_model, F = c->cfg.ffn_hidden, H = c->cfg.n_heads, V = c->cfg.n_structure_heads;
     if (ensure_workspace(c, M)) return 1;
+    if (c->qk_fused && ensure_rope(c, T, st)) return 1;
     const float rs = sqrtf((float)c->cfg.n_layers / 36.0f);
 
     const int rgrid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
@@ -455,9 +481,17 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
             make.xb_out = c->xn;
             const bool last = l == c->cfg.n_layers - 1;           // the final norm + head use the LN kernel
             use.colsum = w.cqkv;
-            if (launch_gemm(c, gemm::EPI_STORE_BF16_LN, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, w.bqkv, 1.f, st, use)) return 1;
-            if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
-            if (launch_attention(c, c->qkv, c->att, B, T, H, st)) return 1;
+            if (c->qk_fused) {
+                // q_ln / k_ln + RoPE inside the QKV epilogue; 1/std of the q and k rows inside attention
+                GemmLN qk = use;
+                qk.rope = c->rope_rows; qk.qk_gamma = w.qk_gamma; qk.qk_sumsq = c->qk_sumsq; qk.T = T; qk.n_rope = 2 * D;
+                if (launch_gemm(c, gemm::EPI_QKV_ROPE_LN, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, w.bqkv, 1.f, st, qk)) return 1;
+                if (launch_attention(c, c->qkv, c->att, B, T, H, c->qk_sumsq, st)) return 1;
+            } else {
+                if (launch_gemm(c, gemm::EPI_STORE_BF16_LN, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, w.bqkv, 1.f, st, use)) return 1;
+                if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
+                if (launch_attention(c, c->qkv, c->att, B, T, H, nullptr, st)) return 1;
+            }
             if (launch_gemm(c, gemm::EPI_RESID_F32_LN, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st, make)) return 1;
             // block 0's geometric attention contributes exactly 0 on this path
             use.colsum = w.c1;
@@ -469,7 +503,7 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
         if (launch_layernorm(c, c->x, w.ln1_w, w.ln1_b, c->xn, M, D, st)) return 1;
         if (launch_gemm(c, gemm::EPI_STORE_BF16, c->xn, w.wqkv, M, 3 * D, D, c->qkv, 3 * D, nullptr, 1.f, st)) return 1;
         if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
-        if (launch_attention(c, c->qkv, c->att, B, T, H, st)) return 1;
+        if (launch_attention(c, c->qkv, c->att, B, T, H, nullptr, st)) return 1;
         if (launch_gemm(c, gemm::EPI_RESID_F32, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st)) return 1;
         // block 0's geometric attention contributes exactly 0 on this path
         if (launch_layernorm(c, c->x, w.ln2_w, w.ln2_b, c->xn, M, D, st)) return 1;
@@ -708,6 +742,8 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_ATTN"))
         c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "tiles") == 0 ? 2 : 0;
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
+    if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
+    c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -839,11 +875,21 @@ int esmdiff_finalize_weights(esmdiff_ctx* c) {
                 return c->fail("finalize_weights: block " + std::to_string(l) + " had a LayerNorm or Linear weight "
                                "replaced after finalize; set attn.layernorm_qkv.{0,1} and ffn.{0,1} of that block together");
             if (!w.cqkv) {
-                if (c->alloc(&w.cqkv, 3 * D) || c->alloc(&w.bqkv, 3 * D) || c->alloc(&w.c1, 2 * F) || c->alloc(&w.b1, 2 * F))
+                if (c->alloc(&w.cqkv, 3 * D) || c->alloc(&w.bqkv, 3 * D) || c->alloc(&w.c1, 2 * F) || c->alloc(&w.b1, 2 * F) ||
+                    c->alloc(&w.qk_gamma, 2 * D))
                     return 1;
             }
+            const float* colmean = nullptr;
+            if (c->qk_fused) {
+                // q_ln / k_ln centring folded into the weight: remove the column means of the q rows
+                // and of the k rows (gemm.cuh EPI_QKV_ROPE_LN)
+                if (!c->colmean && c->alloc(&c->colmean, 2 * D)) return 1;
+                ew::column_mean_kernel<<<dim3((unsigned)((D + 255) / 256), 2), 256>>>(w.wqkv_f32, c->colmean, D, D);
+                colmean = c->colmean;
+            }
             ew::fold_layernorm_weight_kernel<<<(unsigned)((3 * D + 7) / 8), 256>>>(w.wqkv_f32, w.ln1_w, w.ln1_b, w.wqkv,
-                                                                                   w.cqkv, w.bqkv, 3 * D, D, 0);
+                                                                                   w.cqkv, w.bqkv, 3 * D, D, 0, colmean,
+                                                                                   2 * D, D);
             ew::fold_layernorm_weight_kernel<<<(unsigned)((2 * F + 7) / 8), 256>>>(w.w1_f32, w.ln2_w, w.ln2_b, w.w1, w.c1,
                                                                                    w.b1, 2 * F, D, (int)F);
             CK(cudaGetLastError());
@@ -855,6 +901,11 @@ int esmdiff_finalize_weights(esmdiff_ctx* c) {
             w.dirty = false;
         }
     }
+    if (c->qk_fused)
+        for (LayerW& w : c->layers) {            // q_ln / k_ln weights can be replaced without refolding
+            CK(cudaMemcpy(w.qk_gamma, w.qln_w, D * sizeof(float), cudaMemcpyDeviceToDevice));
+            CK(cudaMemcpy(w.qk_gamma + D, w.kln_w, D * sizeof(float), cudaMemcpyDeviceToDevice));
+        }
     ew::default_tracks_kernel<<<(D + 127) / 128, 128>>>(c->plddt_w, c->plddt_b, c->res_w, c->res_b, c->ss8,
                                                         c->sasa, c->const_vec, D);
     CK(cudaGetLastError());
@@ -1074,7 +1125,51 @@ int esmdiff_op_qk_norm_rope(esmdiff_ctx* c, void* qkv, const float* qw, const fl
 int esmdiff_op_attention(esmdiff_ctx* c, const void* qkv, void* out, int B, int T, int H, void* stream) {
     if (!c) return 1;
     CK(cudaSetDevice(c->device));
-    return launch_attention(c, (const bf16*)qkv, (bf16*)out, B, T, H, (cudaStream_t)stream);
+    return launch_attention(c, (const bf16*)qkv, (bf16*)out, B, T, H, nullptr, (cudaStream_t)stream);
+}
+int esmdiff_op_attention_ln(esmdiff_ctx* c, const void* qkv, const float* qk_sumsq, void* out, int B, int T, int H,
+                            void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return launch_attention(c, (const bf16*)qkv, (bf16*)out, B, T, H, qk_sumsq, (cudaStream_t)stream);
+}
+int esmdiff_op_gemm_qkv_rope(esmdiff_ctx* c, const void* a, const void* w, int M, int N, int K, void* out, int64_t ldo,
+                             const float* bias, const void* stats_in, const float* colsum, const float* qk_gamma,
+                             float* qk_sumsq, int T, int n_rope, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    if (ensure_rope(c, T, (cudaStream_t)stream)) return 1;
+    GemmLN ln;
+    ln.stats_in = (const float2*)stats_in;
+    ln.colsum = colsum;
+    ln.rope = c->rope_rows; ln.qk_gamma = qk_gamma; ln.qk_sumsq = qk_sumsq; ln.T = T; ln.n_rope = n_rope;
+    return launch_gemm(c, gemm::EPI_QKV_ROPE_LN, (const bf16*)a, (const bf16*)w, M, N, K, out, ldo, bias, 1.f,
+                       (cudaStream_t)stream, ln);
+}
+int esmdiff_op_fold_layernorm_centered(esmdiff_ctx* c, const float* w, const float* gamma, const float* beta, void* dst,
+                                       float* colsum, float* bias, int64_t rows, int64_t cols, int64_t center_rows,
+                                       int64_t center_block, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    if (center_rows % center_block != 0 || center_rows > rows) return c->fail("fold_layernorm_centered: bad centring blocks");
+    float* cm = nullptr;
+    const int64_t nb = center_rows / center_block;
+    if (nb > 0) {
+        CK(cudaMallocAsync(&cm, nb * cols * sizeof(float), (cudaStream_t)stream));
+        ew::column_mean_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(
+            w, cm, center_block, cols);
+    }
+    ew::fold_layernorm_weight_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        w, gamma, beta, (bf16*)dst, colsum, bias, rows, cols, 0, cm, center_rows, center_block);
+    c->launches += nb > 0 ? 2 : 1;
+    CK(cudaGetLastError());
+    if (cm) CK(cudaFreeAsync(cm, (cudaStream_t)stream));
+    return 0;
+}
+int esmdiff_set_time_conditioning(esmdiff_ctx* c, int on) {
+    if (!c) return 1;
+    c->cfg.time_conditioning = on ? 1 : 0;
+    return 0;
 }
 int esmdiff_op_convert_bf16(esmdiff_ctx* c, const float* src, void* dst, int64_t rows, int64_t cols,
                             int swiglu_hidden, void* stream) {

@@ -23,6 +23,19 @@
 //                       (mean, M2 over each 128-column span) for the NEXT LayerNorm
 //   EPI_STORE_BF16_LN   out = rstd * (acc - mean * c[n]) + b[n]            (QKV projection)
 //   EPI_SWIGLU_BF16_LN  the same on gate and up, then silu(gate) * up      (FFN W1)
+//   EPI_QKV_ROPE_LN     EPI_STORE_BF16_LN for the whole QKV projection with q_ln / k_ln and the
+//                       rotary embedding folded in (SURVEY.md 2.2 k4 + k5; esm MultiHeadAttention:
+//                       q_ln, k_ln = LayerNorm over the FULL width, weight only, then rotate-half
+//                       RoPE per 64-wide head).  The q and k rows of W are CENTRED offline (column
+//                       means over the 1536 q / k output features removed: q - mean(q) is linear in
+//                       the input), so the epilogue holds y = q - mean(q) in fp32.  It writes
+//                       rope(gamma * y) as bf16 and the per-row sum of y^2 over its 128 columns;
+//                       the 1/sqrt(mean y^2 + eps) factor is a per-row scalar that commutes with
+//                       the rotation and is applied inside the attention kernel (query rows: in
+//                       the softmax scale; key rows: on the shared-memory K tile).  Statistics
+//                       come from the fp32 accumulators -- q and k are rounded to bf16 once.
+//                       This removes the stand-alone q/k-LayerNorm + RoPE kernel (5.6 % of a
+//                       step, 12.3 KB of HBM traffic per token row and block).
 // This removes the stand-alone LayerNorm kernel of every block (4 B/element re-read of x and a
 // launch) at the cost of a 2 B/element extra store in the residual epilogue.
 #pragma once
@@ -54,6 +67,7 @@ enum Epilogue {
     EPI_STORE_BF16_LN = 5,
     EPI_RESID_F32_LN = 6,
     EPI_SWIGLU_BF16_LN = 7,
+    EPI_QKV_ROPE_LN = 8,
 };
 constexpr int LN_SPAN = 128;              // columns per partial LayerNorm statistic (= epilogue warp width)
 
@@ -86,6 +100,12 @@ struct Params {
     float2* stats_out;         // EPI_RESID_F32_LN: [M][N / 128] partials of the updated rows
     __nv_bfloat16* xb_out;     // EPI_RESID_F32_LN: bf16 copy of the updated rows, [M][N]
     float ln_eps;
+    // EPI_QKV_ROPE_LN
+    const float* rope;         // [>= T][64]: cos(t f_i) i < 32 | sin(t f_i), token position t = row % T
+    const float* qk_gamma;     // [n_rope]: q_ln.weight | k_ln.weight
+    float* qk_sumsq;           // [M][n_rope / 128]: sum over each 128-column span of (q - mean q)^2, (k - mean k)^2
+    int T;                     // tokens per sample
+    int n_rope;                // columns [0, n_rope) are q | k (multiple of 256); the rest (v) is stored as is
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -210,6 +230,35 @@ __device__ __forceinline__ void st_swz16(uint8_t* box, int row, int chunk, uint3
     *reinterpret_cast<uint4*>(box + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(a, b, c, d);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+// Tile schedule of one CTA pair.  Strided (tile = cluster, cluster + n_clusters, ...) for every
+// epilogue except EPI_QKV_ROPE_LN, which walks a CONTIGUOUS range of the (row tile, column tile)
+// list, column tile fastest: consecutive tiles then share their token rows, and the rotary table
+// row each epilogue thread needs (64 fp32, one row per thread = 32 L1 wavefronts per load
+// instruction) stays in registers across the ~12 q/k column tiles of a row tile instead of being
+// re-read per tile.
+template <int EPI>
+struct TileRange {
+    int begin, end, step;
+    __device__ TileRange(int cluster_id, int num_clusters, int num_tiles) {
+        if constexpr (EPI == EPI_QKV_ROPE_LN) {
+            begin = static_cast<int>(static_cast<long long>(cluster_id) * num_tiles / num_clusters);
+            end = static_cast<int>(static_cast<long long>(cluster_id + 1) * num_tiles / num_clusters);
+            step = 1;
+        } else {
+            begin = cluster_id;
+            end = num_tiles;
+            step = num_clusters;
+        }
+    }
+};
+
 template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] bf16, box 128 x 64
@@ -239,11 +288,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
     const int num_clusters = gridDim.x >> 1;
     const int num_tiles = p.m_tiles * p.n_tiles;
     const int kblocks = p.K / BK;
+    const TileRange<EPI> tr(cluster_id, num_clusters, num_tiles);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_STORE_BF16_LN || EPI == EPI_SWIGLU_BF16_LN) tma_prefetch_desc(&tmC);
+        if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_STORE_BF16_LN || EPI == EPI_SWIGLU_BF16_LN || EPI == EPI_QKV_ROPE_LN) tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -270,7 +320,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
                 const int m0 = (tile / p.n_tiles) * BM + rank * BM_CTA;
                 const int n0 = (tile % p.n_tiles) * BN + rank * BN_CTA;
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -297,7 +347,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
@@ -336,7 +386,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         uint32_t acc_phase = 0;
         constexpr bool RESID = EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN;
         float xres[RESID ? 64 : 1];                   // residual epilogue: two 32-float register sets of x
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        constexpr bool ROPE = EPI == EPI_QKV_ROPE_LN;
+        float rcos[ROPE ? 32 : 1], rsin[ROPE ? 32 : 1];   // rotary table row of this thread's token position
+        int rope_mt = -1;                             // row tile the table row was loaded for
+        for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
             const int nb = tile % p.n_tiles;
             const int n0 = nb * BN + half * (BN / 2);
             const int row_base = (tile / p.n_tiles) * BM + rank * BM_CTA + q * 32;
@@ -402,41 +455,107 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     tma_store_2d(&tmC, box, nb * (BN / 2) + half * 64, row_base);
                     bulk_commit_group();
                 }
-            } else if constexpr (EPI == EPI_STORE_BF16_LN) {
+            } else if constexpr (EPI == EPI_STORE_BF16_LN || EPI == EPI_QKV_ROPE_LN) {
                 // out = rstd * acc + (b[n] - rstd * mean * c[n]); the row statistics are fetched
                 // while the main loop of this tile is still running
                 float rstd, nrm;
                 row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
                               row_base + lane < p.M, p.ln_eps, rstd, nrm);
+                bool rot = false;
+                if constexpr (ROPE) {
+                    rot = n0 < p.n_rope;                           // warp-uniform: a q or k column tile
+                    const int mt = tile / p.n_tiles;
+                    if (rot && mt != rope_mt) {
+                        const int row = row_base + lane < p.M ? row_base + lane : p.M - 1;
+                        const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(row % p.T) * 64);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 c4 = __ldg(rp + i), s4 = __ldg(rp + 8 + i);
+                            rcos[4 * i] = c4.x; rcos[4 * i + 1] = c4.y; rcos[4 * i + 2] = c4.z; rcos[4 * i + 3] = c4.w;
+                            rsin[4 * i] = s4.x; rsin[4 * i + 1] = s4.y; rsin[4 * i + 2] = s4.z; rsin[4 * i + 3] = s4.w;
+                        }
+                        rope_mt = mt;
+                    }
+                }
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
+                if (!rot) {
 #pragma unroll 1
-                for (int c = 0; c < (BN / 2) / 64; ++c) {
-                    if (lane == 0) bulk_wait_group_read<0>();     // the previous store has read the box
-                    __syncwarp();
+                    for (int c = 0; c < (BN / 2) / 64; ++c) {
+                        if (lane == 0) bulk_wait_group_read<0>();     // the previous store has read the box
+                        __syncwarp();
 #pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
-                        uint32_t v[32];
-                        float cs[32], bs[32];
-                        tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
-                        ld_uniform<32>(cs, p.colsum + n0 + c * 64 + hh * 32);
-                        ld_uniform<32>(bs, p.bias + n0 + c * 64 + hh * 32);
-                        tmem_ld_wait();
-                        float y[32];
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t v[32];
+                            float cs[32], bs[32];
+                            tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
+                            ld_uniform<32>(cs, p.colsum + n0 + c * 64 + hh * 32);
+                            ld_uniform<32>(bs, p.bias + n0 + c * 64 + hh * 32);
+                            tmem_ld_wait();
+                            float y[32];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), rstd, fmaf(nrm, cs[j], bs[j]));
+                            for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), rstd, fmaf(nrm, cs[j], bs[j]));
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            st_swz16(box, lane, hh * 4 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
-                                     pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
-                                     pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                            for (int j = 0; j < 4; ++j)
+                                st_swz16(box, lane, hh * 4 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
+                                         pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
+                                         pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, box, n0 + c * 64, row_base);
+                            bulk_commit_group();
+                        }
                     }
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tmC, box, n0 + c * 64, row_base);
-                        bulk_commit_group();
+                } else if constexpr (ROPE) {
+                    // one 64-wide head per staging box: columns d and d + 32 of a head are rotated
+                    // together, 8 rotary frequencies at a time
+                    float sq = 0.f;
+#pragma unroll 1
+                    for (int c = 0; c < (BN / 2) / 64; ++c) {
+                        if (lane == 0) bulk_wait_group_read<0>();
+                        __syncwarp();
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            uint32_t va[8], vb[8];
+                            float ca[8], ba[8], ga[8], cb[8], bb[8], gb[8];
+                            const int na = n0 + c * 64 + g8 * 8;
+                            tmem_ld8(t_row + c * 64 + g8 * 8, va);
+                            tmem_ld8(t_row + c * 64 + 32 + g8 * 8, vb);
+                            ld_uniform<8>(ca, p.colsum + na);
+                            ld_uniform<8>(ba, p.bias + na);
+                            ld_uniform<8>(ga, p.qk_gamma + na);
+                            ld_uniform<8>(cb, p.colsum + na + 32);
+                            ld_uniform<8>(bb, p.bias + na + 32);
+                            ld_uniform<8>(gb, p.qk_gamma + na + 32);
+                            tmem_ld_wait();
+                            float oa[8], ob[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float ya = fmaf(__uint_as_float(va[e]), rstd, fmaf(nrm, ca[e], ba[e]));
+                                const float yb = fmaf(__uint_as_float(vb[e]), rstd, fmaf(nrm, cb[e], bb[e]));
+                                sq = fmaf(ya, ya, sq);
+                                sq = fmaf(yb, yb, sq);
+                                const float za = ya * ga[e], zb = yb * gb[e];
+                                const float cc = rcos[g8 * 8 + e], ss = rsin[g8 * 8 + e];
+                                oa[e] = fmaf(za, cc, -(zb * ss));         // x1 cos - x2 sin
+                                ob[e] = fmaf(zb, cc, za * ss);            // x2 cos + x1 sin
+                            }
+                            st_swz16(box, lane, g8, pack_bf16x2(oa[0], oa[1]), pack_bf16x2(oa[2], oa[3]),
+                                     pack_bf16x2(oa[4], oa[5]), pack_bf16x2(oa[6], oa[7]));
+                            st_swz16(box, lane, 4 + g8, pack_bf16x2(ob[0], ob[1]), pack_bf16x2(ob[2], ob[3]),
+                                     pack_bf16x2(ob[4], ob[5]), pack_bf16x2(ob[6], ob[7]));
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmC, box, n0 + c * 64, row_base);
+                            bulk_commit_group();
+                        }
                     }
+                    if (row_base + lane < p.M)
+                        p.qk_sumsq[static_cast<long long>(row_base + lane) * (p.n_rope / LN_SPAN) + n0 / LN_SPAN] = sq;
                 }
             } else if constexpr (EPI == EPI_SWIGLU_BF16_LN) {
                 float rstd, nrm;
@@ -624,7 +743,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             if (lane == 0) mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[acc]), 0));
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_STORE_BF16_LN || EPI == EPI_SWIGLU_BF16_LN) {
+        if constexpr (EPI == EPI_STORE_BF16 || EPI == EPI_SWIGLU_BF16 || EPI == EPI_STORE_BF16_LN || EPI == EPI_SWIGLU_BF16_LN || EPI == EPI_QKV_ROPE_LN) {
             if (lane == 0) bulk_wait_group<0>();                  // stores complete before exit
         }
     }

@@ -171,7 +171,9 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, const float* 
     if (threadIdx.x == 0) {
         for (int i = 1; i < THREADS / 32; ++i)
             if (red[i] > best || (red[i] == best && red_i[i] < best_i)) { best = red[i]; best_i = red_i[i]; }
-        x[row] = best_i;
+        // no comparison succeeds when every score is NaN (NaN logits): torch.argmax then returns the
+        // first NaN's index, 0 -- never leave an out-of-range id behind for the next embedding lookup
+        x[row] = best_i == 0x7fffffff ? 0 : best_i;
     }
 }
 

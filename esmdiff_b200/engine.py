@@ -80,6 +80,11 @@ class Engine:
         except Exception:
             pass
 
+    def set_time_conditioning(self, on: bool):
+        """MaskedDiffusionLanguageModeling(time_conditioning=...) (model.py:333): False zeroes sigma."""
+        self._check(self.L.esmdiff_set_time_conditioning(self.h, int(bool(on))))
+        self.dims.time_conditioning = bool(on)
+
     def synchronize(self):
         self._check(self.L.esmdiff_synchronize(self.h, _stream()))
 
@@ -240,15 +245,35 @@ class Engine:
                                               _ptr(colsum), _ptr(stats_out), _ptr(xb_out), _stream()))
         return out
 
-    def op_fold_layernorm(self, w, gamma, beta=None, swiglu_hidden=0):
+    def op_fold_layernorm(self, w, gamma, beta=None, swiglu_hidden=0, center_rows=0, center_block=1):
+        """center_rows > 0: column means of each block of ``center_block`` rows are removed from the
+        first ``center_rows`` rows first (q_ln / k_ln centring folded into the QKV weight)."""
         rows, cols = w.shape
         dst = torch.empty(rows, cols, dtype=torch.bfloat16, device=w.device)
         colsum = torch.empty(rows, dtype=torch.float32, device=w.device)
         bias = torch.empty(rows, dtype=torch.float32, device=w.device)
-        self._check(self.L.esmdiff_op_fold_layernorm(self.h, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(dst),
-                                                     _ptr(colsum), _ptr(bias), rows, cols,
-                                                     int(swiglu_hidden), _stream()))
+        if center_rows:
+            assert not swiglu_hidden
+            self._check(self.L.esmdiff_op_fold_layernorm_centered(
+                self.h, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(dst), _ptr(colsum), _ptr(bias), rows, cols,
+                int(center_rows), int(center_block), _stream()))
+        else:
+            self._check(self.L.esmdiff_op_fold_layernorm(self.h, _ptr(w), _ptr(gamma), _ptr(beta), _ptr(dst),
+                                                         _ptr(colsum), _ptr(bias), rows, cols,
+                                                         int(swiglu_hidden), _stream()))
         return dst, colsum, bias
+
+    def op_gemm_qkv_rope(self, a, w, bias, stats_in, colsum, qk_gamma, T, n_rope):
+        """QKV projection with the pre-LN, q_ln / k_ln and RoPE folded in (gemm.cuh epilogue 8).
+        Returns (qkv bf16 [M, N], qk_sumsq fp32 [M, n_rope / 128])."""
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+        sumsq = torch.zeros(M, n_rope // 128, dtype=torch.float32, device=a.device)
+        self._check(self.L.esmdiff_op_gemm_qkv_rope(self.h, _ptr(a), _ptr(w), M, N, K, _ptr(out), out.stride(0),
+                                                    _ptr(bias), _ptr(stats_in), _ptr(colsum), _ptr(qk_gamma),
+                                                    _ptr(sumsq), int(T), int(n_rope), _stream()))
+        return out, sumsq
 
     def op_layernorm(self, x, w, b=None):
         M, D = x.shape
@@ -261,9 +286,16 @@ class Engine:
         self._check(self.L.esmdiff_op_qk_norm_rope(self.h, _ptr(qkv), _ptr(q_w), _ptr(k_w), B, T, D, _stream()))
         return qkv
 
-    def op_attention(self, qkv, B, T, H):
+    def op_attention(self, qkv, B, T, H, qk_sumsq=None):
+        """qk_sumsq None: q, k already normalised + rotated.  Otherwise the un-normalised q', k' and
+        the partial sums of squares of the fused QKV epilogue ([B*T, 2*H*64/128])."""
         out = torch.empty(B * T, H * 64, dtype=torch.bfloat16, device=qkv.device)
-        self._check(self.L.esmdiff_op_attention(self.h, _ptr(qkv), _ptr(out), B, T, H, _stream()))
+        if qk_sumsq is None:
+            self._check(self.L.esmdiff_op_attention(self.h, _ptr(qkv), _ptr(out), B, T, H, _stream()))
+        else:
+            assert qk_sumsq.is_contiguous() and qk_sumsq.shape == (B * T, 2 * H * 64 // 128)
+            self._check(self.L.esmdiff_op_attention_ln(self.h, _ptr(qkv), _ptr(qk_sumsq), _ptr(out), B, T, H,
+                                                       _stream()))
         return out
 
     def op_convert_bf16(self, src, swiglu_hidden=0):

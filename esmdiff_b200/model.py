@@ -62,7 +62,7 @@ class MaskedDiffusionLanguageModeling(nn.Module):
         self.mask_index = MASK
         self.neg_infinity = -1000000.0
         if net is not None:
-            net.engine.dims.time_conditioning = bool(time_conditioning)
+            net.engine.set_time_conditioning(time_conditioning)      # the library zeroes sigma when off (model.py:538-539)
 
     # -- module plumbing ------------------------------------------------------------------------
     @property
@@ -111,6 +111,8 @@ class MaskedDiffusionLanguageModeling(nn.Module):
         ``sigma``: tensor (B,) / (B,1) with one value per sample; the path shares it across the
         batch (ddpm_sample builds it as a constant vector, model.py:571-572)."""
         xt = xt.to(self.device).contiguous()
+        if sequence_tokens is None:
+            sequence_tokens = torch.full_like(xt, 32)      # sequence mask id, the reference's default (net.py:411)
         if sigma is not None:
             sigma = self._process_sigma(torch.as_tensor(sigma))
             s0 = float(sigma.reshape(-1)[0])
@@ -165,8 +167,10 @@ class MaskedDiffusionLanguageModeling(nn.Module):
                 # one draw from torch's CPU generator per call: reproducible under
                 # torch.manual_seed and different for every chunk of a run
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-            return eng.ddpm_sample(seq, x, num_steps, sigma, mc_t, mc_s, seed=seed,
-                                   noise_removal=self.noise_removal)
+            out = eng.ddpm_sample(seq, x, num_steps, sigma, mc_t, mc_s, seed=seed,
+                                  noise_removal=self.noise_removal)
+            eng.synchronize()          # surfaces out-of-range ids (IndexError) / watchdog trips of the loop
+            return out
         B, T = x.shape
         V = self.vocab_size
         logits = torch.empty(B, T, V, dtype=torch.float32, device=self.device)
@@ -177,6 +181,7 @@ class MaskedDiffusionLanguageModeling(nn.Module):
         if self.noise_removal:
             eng.forward_sigma(seq, x, sigma[num_steps], logits_out=logits)
             eng.denoise_argmax(x, logits)
+        eng.synchronize()
         return x
 
     def _ddpm_update(self, x, t, sequence_tokens, dt):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ESMDIFF_ABI_VERSION 1
+#define ESMDIFF_ABI_VERSION 2
 
 #define ESMDIFF_STRUCTURE_MASK_TOKEN 4096 /* esm.utils.constants.esm3.STRUCTURE_MASK_TOKEN; model.py:381 */
 
@@ -48,6 +48,10 @@ const char* esmdiff_last_error(const esmdiff_ctx* ctx); /* ctx may be NULL: last
 /* Replaces hydra.utils.instantiate(cfg.model) + .to(device) (slm/utils/checkpoint_utils.py:59,72). */
 int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out);
 int esmdiff_destroy(esmdiff_ctx* ctx);
+
+/* MaskedDiffusionLanguageModeling(time_conditioning=...) (model.py:333, 538-539) can differ from the
+ * value the network was created with: 0 -> sigma is zeroed before the time embedding. */
+int esmdiff_set_time_conditioning(esmdiff_ctx* ctx, int on);
 
 /* Replaces model.load_state_dict(all_params) (checkpoint_utils.py:63-64).  `key` is the state-dict
  * key of the DeepSpeed ['module'] dict ("net.transformer.blocks.0.attn.out_proj.weight",
@@ -164,6 +168,27 @@ int esmdiff_op_qk_norm_rope(esmdiff_ctx* ctx, void* qkv_bf16_dev, const float* q
 /* ctx bf16 [B*T, D] = softmax(q k^T / 8) v per head, from qkv bf16 [B*T, 3D]. */
 int esmdiff_op_attention(esmdiff_ctx* ctx, const void* qkv_bf16_dev, void* ctx_bf16_dev, int B,
                          int T, int H, void* stream);
+/* The same with q_ln / k_ln and the rotary embedding folded in (esm MultiHeadAttention: LayerNorm
+ * over the full width of q and of k, weight only, then rotate-half RoPE per 64-wide head):
+ *   - esmdiff_op_fold_layernorm_centered: as esmdiff_op_fold_layernorm, with the column means of
+ *     each block of `center_block` rows removed from the first `center_rows` rows first (the q and
+ *     k thirds of the QKV weight), so that the GEMM yields q - mean(q), k - mean(k);
+ *   - esmdiff_op_gemm_qkv_rope: epilogue 8.  out bf16 [M, N]: columns < n_rope hold
+ *     rope(gamma * y) with y the centred, pre-LN-folded projection, the rest (v) y itself;
+ *     qk_sumsq_out fp32 [M, n_rope/128]: sum of y^2 over each 128-column span;
+ *   - esmdiff_op_attention_ln: attention on that layout; 1/sqrt(mean y^2 + eps) of the q and k rows
+ *     is applied inside (qk_sumsq [B*T, 2*H*64/128]: q spans then k spans). */
+int esmdiff_op_fold_layernorm_centered(esmdiff_ctx* ctx, const float* w_dev, const float* gamma_dev,
+                                       const float* beta_dev, void* dst_bf16_dev, float* colsum_dev,
+                                       float* bias_dev, int64_t rows, int64_t cols, int64_t center_rows,
+                                       int64_t center_block, void* stream);
+int esmdiff_op_gemm_qkv_rope(esmdiff_ctx* ctx, const void* a_bf16_dev, const void* w_bf16_dev, int M,
+                             int N, int K, void* out_bf16_dev, int64_t ldo, const float* bias_dev,
+                             const void* stats_in_dev, const float* colsum_dev,
+                             const float* qk_gamma_dev, float* qk_sumsq_out_dev, int T, int n_rope,
+                             void* stream);
+int esmdiff_op_attention_ln(esmdiff_ctx* ctx, const void* qkv_bf16_dev, const float* qk_sumsq_dev,
+                            void* ctx_bf16_dev, int B, int T, int H, void* stream);
 /* fp32 [rows, cols] -> bf16, optional SwiGLU row interleave (swiglu_hidden > 0). */
 int esmdiff_op_convert_bf16(esmdiff_ctx* ctx, const float* src_dev, void* dst_bf16_dev,
                             int64_t rows, int64_t cols, int swiglu_hidden, void* stream);

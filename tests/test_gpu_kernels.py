@@ -243,6 +243,64 @@ def test_attention(engine, B, T, H):
     check(got, ref, 5e-3, 2e-2)
 
 
+@pytest.mark.parametrize("B,T,D", [(3, 60, 1536), (2, 258, 256), (5, 130, 512), (1, 1026, 256), (63, 258, 1536)])
+def test_qkv_epilogue_with_qk_layernorm_and_rope(engine, B, T, D):
+    """gemm.cuh epilogue 8 + the attention kernels' 1/std factors == LayerNorm(x) -> Linear ->
+    q_ln / k_ln -> RoPE -> SDPA in torch fp32 (esm MultiHeadAttention), with non-trivial gamma /
+    beta everywhere.  Checked in two stages: (1) the epilogue's bf16 q', k' times the rstd recovered
+    from its own partial sums against torch's normalised + rotated q, k (and v, and the partial
+    sums themselves against torch); (2) attention on that layout against SDPA."""
+    g = torch.Generator(device=DEV).manual_seed(13 + T)
+    M, H = B * T, D // 64
+    x = torch.randn(M, D, device=DEV, generator=g) * 2 + 0.3
+    x[:, 5] += 40.0
+    gamma = 1.0 + 0.3 * torch.randn(D, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(D, device=DEV, generator=g)
+    qw = 1.0 + 0.3 * torch.randn(D, device=DEV, generator=g)
+    kw = 1.0 + 0.3 * torch.randn(D, device=DEV, generator=g)
+    w = torch.randn(3 * D, D, device=DEV, generator=g) / D ** 0.5
+    w[:D] += 0.02                                                   # q rows with a clear column mean
+    # statistics + bf16 copy of x as the producers leave them (per 128-column span: mean, M2)
+    xs = x.view(M, D // 128, 128)
+    stats = torch.stack([xs.mean(-1), ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)], -1).contiguous()
+    xb = x.bfloat16()
+    wf, cs, bs = engine.op_fold_layernorm(w, gamma, beta, center_rows=2 * D, center_block=D)
+    wc = w.clone()
+    wc[:D] -= wc[:D].mean(0, keepdim=True)
+    wc[D:2 * D] -= wc[D:2 * D].mean(0, keepdim=True)
+    assert rel_fro(wf, wc * gamma) < 3e-3
+    qkv, sumsq = engine.op_gemm_qkv_rope(xb, wf, bs, stats, cs, torch.cat([qw, kw]).contiguous(), T, 2 * D)
+    engine.synchronize()
+    # torch reference, fp32 throughout
+    y = F.layer_norm(x, (D,), gamma, beta, 1e-5) @ w.T
+    q, k, v = y.chunk(3, -1)
+    cos, sin = (z.to(DEV) for z in rotary_tables(T))
+    qr = apply_rotary(F.layer_norm(q, (D,), qw).view(B, T, H, 64), cos, sin).reshape(M, D)
+    kr = apply_rotary(F.layer_norm(k, (D,), kw).view(B, T, H, 64), cos, sin).reshape(M, D)
+    ssq_q = ((q - q.mean(-1, keepdim=True)) ** 2).sum(-1)
+    ssq_k = ((k - k.mean(-1, keepdim=True)) ** 2).sum(-1)
+    nsp = D // 128
+    got_q, got_k = sumsq[:, :nsp].sum(-1), sumsq[:, nsp:].sum(-1)
+    # bf16 operands: each sum of squares carries the operand rounding (~2^-9 / sqrt(D) per term, coherent part small)
+    assert float(((got_q - ssq_q).abs() / ssq_q).max()) < 5e-3
+    assert float(((got_k - ssq_k).abs() / ssq_k).max()) < 5e-3
+    rq = torch.rsqrt(got_q / D + 1e-5)[:, None]
+    rk = torch.rsqrt(got_k / D + 1e-5)[:, None]
+    check(qkv[:, :D].float() * rq, qr, 6e-3, 3e-2)
+    check(qkv[:, D:2 * D].float() * rk, kr, 6e-3, 3e-2)
+    check(qkv[:, 2 * D:], v, 6e-3, 3e-2)
+    att = engine.op_attention(qkv, B, T, H, qk_sumsq=sumsq)
+    engine.synchronize()
+    ref = F.scaled_dot_product_attention(qr.view(B, T, H, 64).transpose(1, 2), kr.view(B, T, H, 64).transpose(1, 2),
+                                         v.view(B, T, H, 64).transpose(1, 2)).transpose(1, 2).reshape(M, D)
+    check(att, ref, 1e-2, 4e-2)
+    # the same attention from the epilogue's OWN rounded operands: isolates the attention kernel
+    qn = (qkv[:, :D].float() * rq).view(B, T, H, 64).transpose(1, 2)
+    kn = (qkv[:, D:2 * D].float() * rk).bfloat16().float().view(B, T, H, 64).transpose(1, 2)
+    ref2 = F.scaled_dot_product_attention(qn, kn, qkv[:, 2 * D:].float().view(B, T, H, 64).transpose(1, 2))
+    check(att, ref2.transpose(1, 2).reshape(M, D), 6e-3, 2.5e-2)
+
+
 def test_attention_permutation_property_full_size(engine):
     """softmax attention is equivariant to permuting the keys/values of a sample: at the config-2
     shape (B=63,T=258,H=24), shuffling the kv rows of every sample leaves the output unchanged

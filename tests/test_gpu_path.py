@@ -3,11 +3,18 @@
 Parity tiers:
   T1  fused sampling kernel == reference `_ddpm_update` tail given identical (logits, u, x):
       token ids bit-exact (documented near-tie exemption, counted).
-  T2  forward vs the fp32 CPU oracle, teacher-forced on the oracle's x_t at every step.
-      Tolerance (written here, measured on B200): bf16 GEMM operands + fp32 accumulate/residual
-      give rel-Frobenius <= 1e-2 on raw logits for the 2-layer tiny model and <= 3e-2 for the
-      48-layer ESM3-open-sized model; masked-row log-probs (post logits_parameterization) within
-      the same relative bound of their spread.
+  T2  forward vs the CPU oracle, teacher-forced on the oracle's x_t.  The contract (BASELINE.json
+      north_star "logits within 1e-3 rel bf16", pinned down by SURVEY.md 8c T2 / section 7 as the
+      POST-logits_parameterization log-probs of masked rows): rel-Frobenius error of the masked-row
+      log-probs < 1e-3, asserted against BOTH oracles:
+        * oracle/esm3_ref.py  -- fp32, what the reference computes;
+        * oracle/esm3_emul.py -- the same weights with a bf16 rounding at exactly the product's
+          rounding points, which separates kernel error from bf16 operand noise.
+      Raw logits are reported and bounded at <= 2x their measured error (PARITY table below).
+      Two implementations with IDENTICAL rounding points that differ only at fp32-ulp level drift
+      3e-3 apart on raw logits after 48 blocks (tests/test_oracle_golden.py measures that floor on
+      CPU), so raw logits cannot be held to 1e-3 against either oracle by any bf16 kernel; the
+      log-prob metric can, and is.
   T3  free-running agreement with the oracle trajectory: reported, not asserted to be 100 %
       (bf16 vs fp32 argmax near-ties diverge; even reference-GPU vs reference-CPU would).
   T4  a reference-style sampler (torch ops, the oracle's restatement of model.py:543-607 --
@@ -19,7 +26,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import esm3_ref, mdlm_ref
+from oracle import esm3_emul, esm3_ref, mdlm_ref
 
 pytestmark = pytest.mark.gpu
 MASK = 4096
@@ -28,6 +35,41 @@ DEV = "cuda"
 
 def rel_fro(a, b):
     return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
+# PARITY bounds: contract 1e-3 on masked-row log-probs; everything else <= 2x what the B200 measured
+# (profiles/r2_parity.md holds the measured values these come from).
+LP_REL_MAX = 1e-3             # masked-row log-probs, rel-Frobenius, vs fp32 oracle and vs bf16-emulating oracle
+RAW_REL_FP32_MAX = 9e-3       # raw logits vs fp32 oracle         (measured 4.1e-3 .. 4.4e-3: bf16 operand noise)
+RAW_REL_EMUL_MAX = 7e-3       # raw logits vs emulating oracle    (measured <= 3.3e-3: drift floor of equal rounding points)
+EMB_REL_FP32_MAX = 5e-3       # pre-final-norm residual stream vs fp32 oracle (measured 2.4e-3)
+
+
+def masked_logp(logits, xt):
+    return mdlm_ref.logits_parameterization(logits.clone(), xt)[xt == MASK][:, :4096]
+
+
+def parity(logits, xt, ref_logits, emul_logits, emb=None, ref_emb=None):
+    """All parity figures of one forward; asserts the bounds above."""
+    logits, xt = logits.float().cpu(), xt.cpu()
+    lp = masked_logp(logits, xt)
+    lp_ref, lp_emu = masked_logp(ref_logits, xt), masked_logp(emul_logits, xt)
+    out = {"lp_rel_fp32": rel_fro(lp, lp_ref), "lp_rel_emul": rel_fro(lp, lp_emu),
+           "lp_maxabs_fp32": float((lp - lp_ref).abs().max()), "lp_maxabs_emul": float((lp - lp_emu).abs().max()),
+           "raw_rel_fp32": rel_fro(logits, ref_logits), "raw_rel_emul": rel_fro(logits, emul_logits),
+           "emul_vs_fp32_raw": rel_fro(emul_logits, ref_logits),
+           "top1_fp32": float((lp.argmax(-1) == lp_ref.argmax(-1)).float().mean()),
+           "top1_emul": float((lp.argmax(-1) == lp_emu.argmax(-1)).float().mean())}
+    if emb is not None:
+        out["emb_rel_fp32"] = rel_fro(emb.float().cpu(), ref_emb)
+        assert out["emb_rel_fp32"] < EMB_REL_FP32_MAX, out
+    assert out["lp_rel_fp32"] < LP_REL_MAX and out["lp_rel_emul"] < LP_REL_MAX, out
+    assert out["raw_rel_fp32"] < RAW_REL_FP32_MAX and out["raw_rel_emul"] < RAW_REL_EMUL_MAX, out
+    return out
+
+
+def fmt(d):
+    return ", ".join(f"{k} {v:.2e}" if v < 0.5 else f"{k} {v:.3f}" for k, v in d.items())
 
 
 def make_seq(B, T, seed=0):
@@ -51,15 +93,16 @@ def test_teacher_forced_trajectory_tiny(tiny_pair, golden_dir):
     assert np.array_equal(np.stack([r["x_t"].numpy() for r in rec]), g["x_t"])
     B = seq.shape[0]
     excused = 0
-    worst = 0.0
+    worst = {}
     agree = []
     for r in rec[:-1]:
         x_t = r["x_t"]
         logits = eng.forward_sigma(seq, x_t.to(DEV), r["sigma_t"])
         eng.synchronize()
-        e = rel_fro(logits.cpu(), r["raw_logits"])
-        worst = max(worst, e)
-        assert e < 1e-2, f"step {r['step']}: logits rel_fro {e:.3e}"                      # T2
+        cond = emb(torch.tensor([r["sigma_t"]]))[0][None, None].expand(B, seq.shape[1], -1)
+        emu = esm3_emul.forward(net, x_t, seq, cond).structure_logits
+        for k, v in parity(logits, x_t, r["raw_logits"], emu).items():                     # T2
+            worst[k] = min(worst.get(k, 1.0), v) if k.startswith("top1") else max(worst.get(k, 0.0), v)
         mct = torch.full((B, 1, 1), r["mc_t"])
         mcs = torch.full((B, 1, 1), r["mc_s"])
         # T1: the kernel on the ORACLE's logits and uniforms
@@ -77,7 +120,7 @@ def test_teacher_forced_trajectory_tiny(tiny_pair, golden_dir):
     got = eng.denoise_argmax(last["x_t"].clone().to(DEV), last["raw_logits"].to(DEV).contiguous())
     eng.synchronize()
     assert torch.equal(got.cpu(), last["x_next"])
-    print(f"\n[T2] worst logits rel_fro {worst:.2e}; [T1] near-tie rows excused {excused}; "
+    print(f"\n[T2 tiny, worst over 25 steps] {fmt(worst)}; [T1] near-tie rows excused {excused}; "
           f"[T3] per-step agreement on own logits min {min(agree):.3f} mean {sum(agree) / len(agree):.3f}")
     assert excused <= 2
     assert sum(agree) / len(agree) > 0.9
@@ -189,8 +232,10 @@ def test_inpainting_tiny(tiny_pair):
 def test_trained_like_layernorm_weights_both_variants():
     """Default init has gamma = 1, beta = 0 in every LayerNorm, which would leave the LayerNorm
     folding (gemm.cuh) and the q_ln/k_ln weights untested end to end: perturb them all, then the
-    folded path (default) and the stand-alone-kernel path (ESMDIFF_LN=separate) must both match
-    the fp32 oracle."""
+    default path (pre-LNs folded through the GEMMs, q_ln / k_ln + RoPE folded into the QKV
+    epilogue and attention), the variant with the stand-alone q/k-LN + RoPE kernel
+    (ESMDIFF_QK=separate) and the all-stand-alone-kernels variant (ESMDIFF_LN=separate) must all
+    match the fp32 oracle, and the default one the bf16-emulating oracle."""
     import os
     from conftest import TINY
     from esmdiff_b200.engine import Dims, Engine
@@ -212,22 +257,29 @@ def test_trained_like_layernorm_weights_both_variants():
     with torch.no_grad():
         cond = emb(torch.tensor([0.7]))[0]
         ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond[None, None].expand(B, T, -1))
+        emu = esm3_emul.forward(net, xt, seq, cond[None, None].expand(B, T, -1))
     errs = {}
-    for mode in ("fold", "separate"):
-        os.environ["ESMDIFF_LN"] = mode
+    for mode, env in (("fused", {}), ("qk_separate", {"ESMDIFF_QK": "separate"}), ("ln_separate", {"ESMDIFF_LN": "separate"})):
+        os.environ.update(env)
         try:
             eng = Engine(Dims(**TINY))
         finally:
-            os.environ.pop("ESMDIFF_LN")
+            for k in env:
+                os.environ.pop(k)
         eng.load_state_dict(sd)
         logits, embd = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(0.7), want_embeddings=True)
         eng.synchronize()
-        errs[mode] = (rel_fro(embd.cpu(), ref.embeddings), rel_fro(logits.cpu(), ref.structure_logits))
+        lp, lp_ref = masked_logp(logits.cpu(), xt), masked_logp(ref.structure_logits, xt)
+        errs[mode] = {"emb_rel_fp32": rel_fro(embd.cpu(), ref.embeddings), "raw_rel_fp32": rel_fro(logits.cpu(), ref.structure_logits),
+                      "lp_rel_fp32": rel_fro(lp, lp_ref)}
+        if mode == "fused":          # the emulating oracle restates the default (fused) product path
+            errs[mode].update(parity(logits, xt, ref.structure_logits, emu.structure_logits, embd, ref.embeddings))
         eng.close()
-    print(f"\n[LN variants] (embeddings, logits) rel_fro: {errs}")
-    for e_emb, e_log in errs.values():
-        assert e_emb < 1e-2 and e_log < 2e-2
-    assert errs["fold"][1] < 1.5 * errs["separate"][1] + 1e-3
+    print("\n[LayerNorm variants, trained-like gamma/beta] " + "; ".join(f"{m}: {fmt(e)}" for m, e in errs.items()))
+    for e in errs.values():
+        assert e["emb_rel_fp32"] < EMB_REL_FP32_MAX and e["raw_rel_fp32"] < RAW_REL_FP32_MAX and e["lp_rel_fp32"] < LP_REL_MAX
+    # folding q_ln / k_ln into the epilogue removes one bf16 rounding of q and k: it must not be worse
+    assert errs["fused"]["raw_rel_fp32"] < 1.5 * errs["ln_separate"]["raw_rel_fp32"] + 1e-3
 
 
 # ---------------------------------------------------------------------------------------------
@@ -245,34 +297,63 @@ def full_model():
     eng.close()
 
 
-def test_full_size_forward_vs_oracle(full_model):
-    """T2 at the real architecture (config-1 shape B=4 -> here B=2, T=60 so the fp32 CPU oracle
-    finishes in seconds)."""
-    eng, sd = full_model
-    net, emb = esm3_ref.build_from_state_dict(esm3_ref.Esm3Dims(), sd)
-    B, T = 2, 60
-    seq = make_seq(B, T, seed=1)
+@pytest.fixture(scope="module")
+def full_oracle(full_model):
+    """fp32 oracle modules holding the same tensors as the engine (built once: 1.4 B parameters)."""
+    _, sd = full_model
+    return esm3_ref.build_from_state_dict(esm3_ref.Esm3Dims(), sd)
+
+
+BPTI = "RPDFCLEPPYTGPCKARIIRYFYNAKAGLCQTFVYGGCRAKRNNFKSAEDCMRTCGGA"      # data/targets/bpti/bpti.pdb, 58 residues
+
+
+def _case(name):
+    """(seq (B,T), x_t (B,T), sigma) of the BASELINE configurations, teacher-forced mid-trajectory."""
+    from esmdiff_b200.sampling import build_prior
+    from esmdiff_b200.tokenization import tokenize_sequence
     g = torch.Generator().manual_seed(2)
-    xt = torch.randint(0, 4096, (B, T), generator=g)
-    xt[torch.rand(B, T, generator=g) < 0.5] = MASK
-    sigma = 0.9
+    if name == "config1_bpti_B4_T60":
+        seq = tokenize_sequence(BPTI)[None].repeat(4, 1)
+    elif name == "config3_B1_T514":
+        seq = make_seq(1, 514, seed=3)
+    else:
+        seq = make_seq(2, 258, seed=1)
+    B, T = seq.shape
+    if name == "config4_inpaint_B2_T258":
+        # sample_esmdiff.py:197-201 + models/utils.py:117-123: token positions 1..32 masked in the prior,
+        # residues 1..32 ('_' -> id 32) masked in the sequence (the reference's off-by-one, kept)
+        seq = seq.clone()
+        seq[:, 2:34] = 32
+        st = torch.randint(0, 4096, (T,), generator=g)
+        st[0], st[-1] = 4098, 4097
+        xt = build_prior(st, B, mask_ids=list(range(1, 33)))
+        sigma = 6.9                                   # first step of the grid: t = 1 (model.py:564-567)
+    else:
+        xt = torch.randint(0, 4096, (B, T), generator=g)
+        xt[torch.rand(B, T, generator=g) < 0.5] = MASK
+        sigma = 0.9
+    return seq, xt, sigma
+
+
+@pytest.mark.parametrize("name", ["config1_bpti_B4_T60", "config2_B2_T258", "config3_B1_T514",
+                                  "config4_inpaint_B2_T258"])
+def test_full_size_forward_vs_oracles(full_model, full_oracle, name):
+    """T2 at the real architecture (d=1536, 48 blocks, 24 heads) and at the sequence lengths of
+    every BASELINE configuration: T = 60 (one partial query tile), T = 258 (two query tiles + the
+    two CUDA-core trailing rows, five K/V tiles, 8-9 GEMM row tiles) and T = 514 (four query tiles,
+    nine K/V tiles); config 4's partially masked prior with masked sequence residues."""
+    eng, _ = full_model
+    net, emb = full_oracle
+    seq, xt, sigma = _case(name)
+    B, T = seq.shape
     with torch.no_grad():
-        cond = emb(torch.tensor([sigma]))[0]
-        ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond[None, None].expand(B, T, -1))
+        cond = emb(torch.tensor([sigma]))[0][None, None].expand(B, T, -1)
+        ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond)
+        emu = esm3_emul.forward(net, xt, seq, cond)
     logits, embd = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(sigma), want_embeddings=True)
     eng.synchronize()
-    e_emb = rel_fro(embd.cpu(), ref.embeddings)
-    e_log = rel_fro(logits.cpu(), ref.structure_logits)
-    m = xt == MASK
-    lp_ref = mdlm_ref.logits_parameterization(ref.structure_logits.clone(), xt)[m][:, :4096]
-    lp_got = mdlm_ref.logits_parameterization(logits.cpu().clone(), xt)[m][:, :4096]
-    e_lp = float((lp_got - lp_ref).abs().max())
-    spread = float(lp_ref.max() - lp_ref.min())
-    top1 = float((lp_got.argmax(-1) == lp_ref.argmax(-1)).float().mean())
-    print(f"\n[T2 full size] embeddings rel_fro {e_emb:.2e}, logits rel_fro {e_log:.2e}, "
-          f"masked-row log-prob max abs err {e_lp:.3e} (spread {spread:.2f}), argmax agreement {top1:.3f}")
-    assert e_emb < 1e-2 and e_log < 3e-2
-    assert e_lp < 3e-2 * max(spread, 1.0)
+    out = parity(logits, xt, ref.structure_logits, emu.structure_logits, embd, ref.embeddings)
+    print(f"\n[T2 full size {name}] {fmt(out)}")
 
 
 def test_config2_full_run_properties(full_model):

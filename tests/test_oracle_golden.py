@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import esm3_ref, mdlm_ref, ref_loader
+from oracle import esm3_emul, esm3_ref, mdlm_ref, ref_loader
 
 MASK = 4096
 
@@ -133,6 +133,65 @@ def test_oracle_net_structure():
     b = net(structure_tokens=xt2, sequence_tokens=seq).structure_logits
     assert torch.equal(a, b) and a.shape == (1, 5, 4101)
     assert esm3_ref.forward_flops(1, 258) == 258 * (48 * (56623104 + 6144 * 258) + 17316864)
+
+
+def test_rotary_matches_flash_attn():
+    """Second anchor for the unpinned network half: esm/layers/rotary.py is the
+    flash-attn rotary module (rotate-half, non-interleaved, inv_freq = base^(-2i/d), fp32 tables);
+    the copy installed in this image (flash_attn/layers/rotary.py:14-33 + RotaryEmbedding's
+    inv_freq / cos-sin cache) must agree with the oracle's restatement bit for bit."""
+    fr = pytest.importorskip("flash_attn.layers.rotary")
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 37, 3, 64, generator=g)
+    cos, sin = esm3_ref.rotary_tables(37, 64)
+    inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 64, 2, dtype=torch.float32) / 64))     # RotaryEmbedding._compute_inv_freq
+    freqs = torch.outer(torch.arange(37, dtype=torch.float32), inv_freq)                # _update_cos_sin_cache
+    assert torch.equal(cos, torch.cos(freqs)) and torch.equal(sin, torch.sin(freqs))
+    assert torch.equal(esm3_ref.apply_rotary(x, cos, sin), fr.apply_rotary_emb_torch(x, cos, sin, interleaved=False))
+    rot = fr.rotate_half(x)
+    assert torch.equal(rot[..., :32], -x[..., 32:]) and torch.equal(rot[..., 32:], x[..., :32])
+
+
+def _masked_logp(logits, xt):
+    return mdlm_ref.logits_parameterization(logits.clone(), xt)[xt == MASK][:, :4096]
+
+
+def test_bf16_emulating_oracle():
+    """oracle/esm3_emul.py: all rounding points off == the fp32 oracle (same algebra: LayerNorms
+    folded through the Linears, q_ln / k_ln centring in the weight, 1/std applied to the scores,
+    online softmax in 64-key tiles); all on == bf16 noise of the expected size.  Also measures, on
+    CPU, how far two implementations with IDENTICAL rounding points drift apart when they differ
+    only at fp32-ulp level (float64 vs fp32 accumulation): that drift, not 0, is the floor of any
+    product-vs-emulation comparison."""
+    dims = esm3_ref.Esm3Dims(d_model=256, n_heads=4, v_heads=8, n_layers=3)
+    net, emb = esm3_ref.build_reference_model(dims, seed=2)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for name, prm in net.named_parameters():            # non-trivial LayerNorm weights and biases
+            if prm.dim() == 1 and "head.0.bias" not in name and "head.3.bias" not in name:
+                prm.mul_(1 + 0.2 * torch.randn(prm.shape, generator=g)) if name.endswith("weight") \
+                    else prm.add_(0.1 * torch.randn(prm.shape, generator=g))
+    B, T = 2, 130                                            # T = 128 + 2: exercises the trailing-row path
+    seq = torch.cat([torch.zeros(1, dtype=torch.long), torch.randint(4, 24, (T - 2,), generator=g),
+                     torch.full((1,), 2)])[None].repeat(B, 1)
+    xt = torch.randint(0, 4096, (B, T), generator=g)
+    xt[torch.rand(B, T, generator=g) < 0.5] = MASK
+    cond = emb(torch.tensor([0.8]))[0][None, None].expand(B, T, -1)
+    ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    off = esm3_emul.forward(net, xt, seq, cond, esm3_emul.Rounding.none())
+    assert rel(off.structure_logits, ref.structure_logits) < 2e-5 and rel(off.embeddings, ref.embeddings) < 1e-5
+    budget = esm3_emul.error_budget(
+        net, xt, seq, cond,
+        lambda o, r: (rel(o.structure_logits, r.structure_logits),
+                      rel(_masked_logp(o.structure_logits, xt), _masked_logp(r.structure_logits, xt))))
+    print("\n[bf16 emulation, 3 layers d=256] (raw logits rel, masked log-prob rel) per rounding point:",
+          {k: (round(a, 5), round(b, 6)) for k, (a, b) in budget.items()})
+    assert 5e-4 < budget["all"][0] < 1.5e-2                 # bf16 operands: a few 1e-3 on raw logits
+    assert budget["all"][1] < 1e-3                           # the path's contract metric (SURVEY.md 8c T2)
+    for k in ("weights", "act", "qkv", "k_prescale", "p"):
+        assert 0 < budget[k][0] <= 1.2 * budget["all"][0] + 1e-4
+    assert budget["f64_drift"][1] < 1e-3                     # ... and it is well-posed: the drift stays below it
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the build container")
