@@ -30,7 +30,7 @@ class Cfg(C.Structure):
                 ("ffn_hidden", C.c_int32), ("n_structure_heads", C.c_int32),
                 ("seq_vocab", C.c_int32), ("struct_vocab", C.c_int32),
                 ("time_freq_dim", C.c_int32), ("time_conditioning", C.c_int32),
-                ("reserved", C.c_int32 * 7)]
+                ("model_kind", C.c_int32), ("n_aux_out", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 def _sources():
@@ -99,6 +99,7 @@ _SIGS = {
     "esmdiff_op_attention": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "esmdiff_op_convert_bf16": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "esmdiff_set_time_conditioning": (C.c_int, [_P, C.c_int]),
+    "esmdiff_decode_structure": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "esmdiff_op_fold_layernorm_centered": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64,
                                                      C.c_int64, C.c_int64, _P]),
     "esmdiff_op_gemm_qkv_rope": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P,

@@ -69,10 +69,11 @@ def instantiate(node, **overrides):
 
 
 def load_model_cfg(ckpt_path: Path) -> dict:
-    if ckpt_path.is_dir():
-        cfg_path = ckpt_path.parent.parent.parent / ".hydra/config.yaml"
-    else:
-        cfg_path = ckpt_path.parent.parent / ".hydra/config.yaml"
+    """The ``model:`` block of the run's ``.hydra/config.yaml``, two levels above the checkpoint --
+    the same directory for a single-file checkpoint and for a DeepSpeed checkpoint DIRECTORY
+    (reference checkpoint_utils.py:45-49: four parents of ``dir/checkpoint/mp_rank_00_model_states.pt``
+    = two parents of ``dir``) -- else ``configs/experiment/mdlm.yaml``, else the built-in copy of it."""
+    cfg_path = ckpt_path.parent.parent / ".hydra/config.yaml"
     candidates = [cfg_path, Path("configs/experiment/mdlm.yaml")]
     for p in candidates:
         if p.exists():
@@ -83,13 +84,35 @@ def load_model_cfg(ckpt_path: Path) -> dict:
     return dict(DEFAULT_MODEL_CFG)
 
 
-def build_model(model_cfg: dict | None = None, device=None, **net_overrides):
+# Keys of the model: block that only matter for training.  A run's composed .hydra/config.yaml
+# carries configs/model/default.yaml underneath the experiment: ``optimizer`` / ``scheduler`` are
+# ``_partial_`` torch / transformers factories there, and ``net.config`` is the T5 baseline's
+# ``transformers.T5Config`` block, which ``CustomizedESM3.__init__(..., *args, **kwargs)`` swallows
+# unused (net.py:323-334).  None of them is instantiated here.
+TRAINING_ONLY_KEYS = ("optimizer", "scheduler", "compile")
+NET_KEYS = ("d_model", "n_heads", "v_heads", "n_layers", "pretrained", "n_structure_heads", "n_sequence_heads")
+
+
+def split_model_cfg(model_cfg: dict | None) -> tuple[dict, dict]:
+    """(model kwargs incl. nested ``_target_`` nodes, CustomizedESM3 kwargs) from a ``model:`` block."""
     cfg = dict(model_cfg or DEFAULT_MODEL_CFG)
-    net_cfg = dict(cfg.pop("net"))
-    net_cfg.pop("_target_", None)
-    net = _net.CustomizedESM3(**{k: _coerce(v) for k, v in net_cfg.items()}, device=device,
-                              time_conditioning=bool(cfg.get("time_conditioning", False)),
-                              **net_overrides)
+    target = cfg.get("_target_", "slm.models.model.MaskedDiffusionLanguageModeling")
+    if target != "slm.models.model.MaskedDiffusionLanguageModeling":
+        raise ValueError(f"the ddpm path samples MaskedDiffusionLanguageModeling checkpoints, not {target}")
+    for k in TRAINING_ONLY_KEYS:
+        cfg.pop(k, None)
+    net_cfg = dict(cfg.pop("net", None) or {})
+    nt = net_cfg.pop("_target_", "slm.models.net.CustomizedESM3")
+    if nt != "slm.models.net.CustomizedESM3":
+        raise ValueError(f"unsupported net on the ddpm path: {nt}")
+    net_kwargs = {k: _coerce(v) for k, v in net_cfg.items() if k in NET_KEYS}
+    return cfg, net_kwargs
+
+
+def build_model(model_cfg: dict | None = None, device=None, **net_overrides):
+    cfg, net_kwargs = split_model_cfg(model_cfg)
+    net_kwargs.update(net_overrides)
+    net = _net.CustomizedESM3(**net_kwargs, device=device, time_conditioning=bool(cfg.get("time_conditioning", False)))
     return instantiate(cfg, net=net)
 
 

@@ -17,6 +17,7 @@
 
 #include "attention.cuh"
 #include "attention_resident.cuh"
+#include "decoder.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -74,6 +75,11 @@ struct esmdiff_ctx {
     float *norm_w = nullptr, *h0_b = nullptr, *h2_w = nullptr, *h2_b = nullptr, *h3_b = nullptr;
     bf16 *h0_w = nullptr, *h3_w = nullptr;
     float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
+    // model_kind 1 (VQ-VAE structure token decoder): token embedding and the pLDDT regression head;
+    // h0/h2/h3 above then hold Dim6RotStructureHead's ffn1 / norm / proj
+    float *dec_embed = nullptr, *p0_b = nullptr, *p2_w = nullptr, *p2_b = nullptr, *p3_b = nullptr;
+    bf16 *p0_w = nullptr, *p3_w = nullptr;
+    float* aux_ws = nullptr;                           // [rows][n_aux_out] pLDDT logits
     std::set<std::string> loaded;
     bool finalized = false;
     std::vector<void*> owned;
@@ -416,7 +422,7 @@ static int launch_time_embed(esmdiff_ctx* c, float sigma, float* cond, cudaStrea
 static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     if (M <= c->ws_rows) return 0;
     // free the previous workspace buffers
-    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf, c->stats, c->qk_sumsq};
+    void* olds[] = {c->x, c->headh, c->logits_ws, c->xn, c->qkv, c->att, c->hbuf, c->stats, c->qk_sumsq, c->aux_ws};
     for (void* o : olds)
         if (o) {
             cudaFree(o);
@@ -430,6 +436,8 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr; c->stats = nullptr; c->qk_sumsq = nullptr;
     if (c->alloc(&c->stats, M * (D / 128))) return 1;
     if (c->alloc(&c->qk_sumsq, M * 2 * (D / 128))) return 1;
+    c->aux_ws = nullptr;
+    if (c->cfg.n_aux_out > 0 && c->alloc(&c->aux_ws, M * c->cfg.n_aux_out)) return 1;
     if (c->alloc(&c->x, M * D)) return 1;
     if (c->alloc(&c->headh, M * D)) return 1;
     if (c->alloc(&c->logits_ws, M * V)) return 1;
@@ -442,33 +450,15 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward
+// transformer blocks (esm UnifiedTransformerBlock without geometric attention), shared by the
+// sampling network (48 x d=1536, residual / sqrt(48/36)) and the structure token decoder
+// (30 x d=1280, scale_residue=False).  In: c->x (fp32 stream) and, with the LayerNorms folded,
+// c->xn (bf16 copy) + c->stats.  Out: c->x.
 // ------------------------------------------------------------------------------------------------
-static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T,
-                        const float* aux, int64_t aux_stride, float* logits, float* emb_out,
-                        cudaStream_t st) {
-    if (!c->finalized) return c->fail("forward: esmdiff_finalize_weights has not succeeded");
-    if (B <= 0 || T <= 0) return c->fail("forward: B and T must be positive");
-    const int64_t M64 = (int64_t)B * T;
-    if (M64 > (1ll << 30)) return c->fail("forward: B*T too large");
-    const int M = (int)M64;
-    const int D = c->cfg.d_model, F = c->cfg.ffn_hidden, H = c->cfg.n_heads, V = c->cfg.n_structure_heads;
-    if (ensure_workspace(c, M)) return 1;
-    if (c->qk_fused && ensure_rope(c, T, st)) return 1;
-    const float rs = sqrtf((float)c->cfg.n_layers / 36.0f);
-
-    const int rgrid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
-    {
-    ProfScope prof(c, ESMDIFF_PROF_EMBED, 12.0 * M * D, st);
-    ew::embed_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const long long*>(seq),
-                                            reinterpret_cast<const long long*>(xt), c->seq_embed,
-                                            c->struct_embed, c->const_vec, aux, aux_stride, c->x, M, D,
-                                            c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err,
-                                            c->ln_fold ? c->xn : nullptr, c->stats);
-    }
-    c->launches++;
-    CK(cudaGetLastError());
-
+static int run_blocks(esmdiff_ctx* c, int B, int T, cudaStream_t st) {
+    const int M = B * T;
+    const int D = c->cfg.d_model, F = c->cfg.ffn_hidden, H = c->cfg.n_heads;
+    const float rs = c->cfg.model_kind == 1 ? 1.0f : sqrtf((float)c->cfg.n_layers / 36.0f);
     for (int l = 0; l < c->cfg.n_layers; ++l) {
         const LayerW& w = c->layers[l];
         if (c->ln_fold) {
@@ -510,6 +500,38 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
         if (launch_gemm(c, gemm::EPI_SWIGLU_BF16, c->xn, w.w1, M, 2 * F, D, c->hbuf, F, nullptr, 1.f, st)) return 1;
         if (launch_gemm(c, gemm::EPI_RESID_F32, c->hbuf, w.w2, M, D, F, c->x, D, nullptr, rs, st)) return 1;
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T,
+                        const float* aux, int64_t aux_stride, float* logits, float* emb_out,
+                        cudaStream_t st) {
+    if (!c->finalized) return c->fail("forward: esmdiff_finalize_weights has not succeeded");
+    if (B <= 0 || T <= 0) return c->fail("forward: B and T must be positive");
+    const int64_t M64 = (int64_t)B * T;
+    if (M64 > (1ll << 30)) return c->fail("forward: B*T too large");
+    const int M = (int)M64;
+    const int D = c->cfg.d_model, V = c->cfg.n_structure_heads;
+    if (ensure_workspace(c, M)) return 1;
+    if (c->qk_fused && ensure_rope(c, T, st)) return 1;
+    if (c->cfg.model_kind != 0) return c->fail("forward: this context holds a structure token decoder (esmdiff_decode_structure)");
+
+    const int rgrid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
+    {
+    ProfScope prof(c, ESMDIFF_PROF_EMBED, 12.0 * M * D, st);
+    ew::embed_kernel<<<rgrid, 256, 0, st>>>(reinterpret_cast<const long long*>(seq),
+                                            reinterpret_cast<const long long*>(xt), c->seq_embed,
+                                            c->struct_embed, c->const_vec, aux, aux_stride, c->x, M, D,
+                                            c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err,
+                                            c->ln_fold ? c->xn : nullptr, c->stats);
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+
+    if (run_blocks(c, B, T, st)) return 1;
     if (emb_out) CK(cudaMemcpyAsync(emb_out, c->x, (size_t)M * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (launch_layernorm(c, c->x, c->norm_w, nullptr, c->xn, M, D, st)) return 1;
     if (launch_gemm(c, gemm::EPI_BIAS_GELU_F32, c->xn, c->h0_w, M, D, D, c->headh, D, c->h0_b, 1.f, st)) return 1;
@@ -613,6 +635,37 @@ static bool resolve_key(esmdiff_ctx* c, const std::string& key, Slot* s) {
     auto f32 = [&](float** p, std::vector<int64_t> shp) { *s = {K_F32, (void**)p, shp}; return true; };
     auto b16 = [&](bf16** p, std::vector<int64_t> shp) { *s = {K_BF16, (void**)p, shp}; return true; };
     auto skip = [&]() { *s = {K_SKIP, nullptr, {}}; return true; };
+    std::string k;
+    if (c->cfg.model_kind == 1) {
+        // StructureTokenDecoder.state_dict() names
+        const int64_t A = c->cfg.n_aux_out;
+        if (key == "embed.weight") return f32(&c->dec_embed, {c->cfg.struct_vocab, D});
+        if (key == "decoder_stack.norm.weight") return f32(&c->norm_w, {D});
+        if (key.rfind("affine_output_projection.", 0) == 0) {
+            const std::string r = key.substr(25);
+            if (r == "ffn1.weight") return b16(&c->h0_w, {D, D});
+            if (r == "ffn1.bias") return f32(&c->h0_b, {D});
+            if (r == "norm.weight") return f32(&c->h2_w, {D});
+            if (r == "norm.bias") return f32(&c->h2_b, {D});
+            if (r == "proj.weight") return b16(&c->h3_w, {V, D});
+            if (r == "proj.bias") return f32(&c->h3_b, {V});
+            return false;
+        }
+        if (key.rfind("plddt_head.", 0) == 0) {
+            if (A == 0) return skip();
+            const std::string r = key.substr(11);
+            if (r == "0.weight") return b16(&c->p0_w, {D, D});
+            if (r == "0.bias") return f32(&c->p0_b, {D});
+            if (r == "2.weight") return f32(&c->p2_w, {D});
+            if (r == "2.bias") return f32(&c->p2_b, {D});
+            if (r == "3.weight") return b16(&c->p3_w, {A, D});
+            if (r == "3.bias") return f32(&c->p3_b, {A});
+            return false;
+        }
+        if (key.rfind("pairwise_classification_head.", 0) == 0) return skip();     // pTM / PAE: not on this path
+        if (key.rfind("decoder_stack.", 0) != 0) return false;
+        k = "transformer." + key.substr(14);
+    } else
     if (key.rfind("sigma_embedder.mlp.", 0) == 0) {
         const std::string r = key.substr(19);
         if (r == "0.weight") return f32(&c->te_w0, {D, c->cfg.time_freq_dim});
@@ -621,8 +674,10 @@ static bool resolve_key(esmdiff_ctx* c, const std::string& key, Slot* s) {
         if (r == "2.bias") return f32(&c->te_b2, {D});
         return false;
     }
-    if (key.rfind("net.", 0) != 0) return false;
-    const std::string k = key.substr(4);
+    if (c->cfg.model_kind == 0) {
+        if (key.rfind("net.", 0) != 0) return false;
+        k = key.substr(4);
+    }
     if (k == "encoder.sequence_embed.weight") return f32(&c->seq_embed, {c->cfg.seq_vocab, D});
     if (k == "encoder.structure_tokens_embed.weight") return f32(&c->struct_embed, {c->cfg.struct_vocab, D});
     if (k == "encoder.plddt_projection.weight") return f32(&c->plddt_w, {D, 16});
@@ -678,6 +733,22 @@ static bool resolve_key(esmdiff_ctx* c, const std::string& key, Slot* s) {
 }
 
 static std::vector<std::string> required_keys(const esmdiff_ctx* c) {
+    const char* per_block[] = {"attn.layernorm_qkv.0.weight", "attn.layernorm_qkv.0.bias",
+                               "attn.layernorm_qkv.1.weight", "attn.q_ln.weight", "attn.k_ln.weight",
+                               "attn.out_proj.weight", "ffn.0.weight", "ffn.0.bias", "ffn.1.weight",
+                               "ffn.3.weight"};
+    if (c->cfg.model_kind == 1) {
+        std::vector<std::string> k = {"embed.weight", "decoder_stack.norm.weight",
+                                      "affine_output_projection.ffn1.weight", "affine_output_projection.ffn1.bias",
+                                      "affine_output_projection.norm.weight", "affine_output_projection.norm.bias",
+                                      "affine_output_projection.proj.weight", "affine_output_projection.proj.bias"};
+        if (c->cfg.n_aux_out > 0)
+            for (const char* r : {"0.weight", "0.bias", "2.weight", "2.bias", "3.weight", "3.bias"})
+                k.push_back(std::string("plddt_head.") + r);
+        for (int l = 0; l < c->cfg.n_layers; ++l)
+            for (const char* r : per_block) k.push_back("decoder_stack.blocks." + std::to_string(l) + "." + r);
+        return k;
+    }
     std::vector<std::string> k = {
         "net.encoder.sequence_embed.weight", "net.encoder.structure_tokens_embed.weight",
         "net.encoder.plddt_projection.weight", "net.encoder.plddt_projection.bias",
@@ -712,8 +783,11 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     *out = nullptr;
     if (cfg->d_model <= 0 || cfg->d_model % 256 != 0 || cfg->d_model > 1536 ||
         cfg->n_heads * 64 != cfg->d_model || cfg->n_layers <= 0 || cfg->ffn_hidden % 128 != 0 ||
-        cfg->ffn_hidden <= 0 || cfg->n_structure_heads <= ESMDIFF_STRUCTURE_MASK_TOKEN ||
-        cfg->n_structure_heads > 4352 || cfg->time_freq_dim <= 0 || cfg->time_freq_dim % 2 != 0) {
+        cfg->ffn_hidden <= 0 || cfg->model_kind < 0 || cfg->model_kind > 1 ||
+        (cfg->model_kind == 0 && (cfg->n_structure_heads <= ESMDIFF_STRUCTURE_MASK_TOKEN ||
+                                  cfg->n_structure_heads > 4352 || cfg->time_freq_dim <= 0 || cfg->time_freq_dim % 2 != 0)) ||
+        (cfg->model_kind == 1 && (cfg->n_structure_heads < 9 || cfg->n_structure_heads > 4352 || cfg->n_aux_out < 0 ||
+                                  cfg->n_aux_out > 4352 || cfg->struct_vocab <= 0))) {
         g_create_error = "create: unsupported dimensions (need d_model % 256 == 0 <= 1536, d_head 64, "
                          "ffn_hidden % 128 == 0, 4096 < n_structure_heads <= 4352)";
         return 1;
@@ -906,8 +980,9 @@ int esmdiff_finalize_weights(esmdiff_ctx* c) {
             CK(cudaMemcpy(w.qk_gamma, w.qln_w, D * sizeof(float), cudaMemcpyDeviceToDevice));
             CK(cudaMemcpy(w.qk_gamma + D, w.kln_w, D * sizeof(float), cudaMemcpyDeviceToDevice));
         }
-    ew::default_tracks_kernel<<<(D + 127) / 128, 128>>>(c->plddt_w, c->plddt_b, c->res_w, c->res_b, c->ss8,
-                                                        c->sasa, c->const_vec, D);
+    if (c->cfg.model_kind == 0)
+        ew::default_tracks_kernel<<<(D + 127) / 128, 128>>>(c->plddt_w, c->plddt_b, c->res_w, c->res_b, c->ss8,
+                                                            c->sasa, c->const_vec, D);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     c->finalized = true;
@@ -1006,6 +1081,54 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
         if (forward_step(c, seq, out, B, T, c->logits_ws, st)) return 1;
         if (launch_sampler<1>(c, c->logits_ws, nullptr, out, nullptr, M, 0.f, 0.f, 0, 0, st)) return 1;
     }
+    return 0;
+}
+
+int esmdiff_decode_structure(esmdiff_ctx* c, const int64_t* tokens, int B, int T, float* bb_out, float* o_out,
+                             float* plddt_out, float* affine_out, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    if (c->cfg.model_kind != 1) return c->fail("decode_structure: context was not created as a structure token decoder");
+    if (!c->finalized) return c->fail("decode_structure: esmdiff_finalize_weights has not succeeded");
+    if (B <= 0 || T < 3 || !tokens || !bb_out) return c->fail("decode_structure: bad arguments (T counts BOS and EOS)");
+    if (plddt_out && c->cfg.n_aux_out == 0) return c->fail("decode_structure: this decoder has no pLDDT head");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t M64 = (int64_t)B * T;
+    if (M64 > (1ll << 30)) return c->fail("decode_structure: B*T too large");
+    const int M = (int)M64;
+    const int D = c->cfg.d_model, V = c->cfg.n_structure_heads;
+    if (ensure_workspace(c, M)) return 1;
+    if (c->qk_fused && ensure_rope(c, T, st)) return 1;
+    {
+        ProfScope prof(c, ESMDIFF_PROF_EMBED, 6.0 * M * D, st);
+        dec::embed_tokens_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(tokens), c->dec_embed, c->x,
+                                                             c->ln_fold ? c->xn : nullptr, c->stats, M, D,
+                                                             c->cfg.struct_vocab, c->dev_err);
+    }
+    c->launches++;
+    CK(cudaGetLastError());
+    if (run_blocks(c, B, T, st)) return 1;
+    if (launch_layernorm(c, c->x, c->norm_w, nullptr, c->xn, M, D, st)) return 1;
+    // Dim6RotStructureHead: ffn1 + GELU, LayerNorm, proj (same graph as a RegressionHead)
+    if (launch_gemm(c, gemm::EPI_BIAS_GELU_F32, c->xn, c->h0_w, M, D, D, c->headh, D, c->h0_b, 1.f, st)) return 1;
+    if (launch_layernorm(c, c->headh, c->h2_w, c->h2_b, c->att, M, D, st)) return 1;
+    if (launch_gemm(c, gemm::EPI_BIAS_F32, c->att, c->h3_w, M, V, D, c->logits_ws, V, c->h3_b, 1.f, st)) return 1;
+    dec::backbone_frames_kernel<<<(M + 127) / 128, 128, 0, st>>>(c->logits_ws, V, bb_out, M);
+    c->launches++;
+    if (affine_out) CK(cudaMemcpyAsync(affine_out, c->logits_ws, (size_t)M * V * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (o_out) {
+        dec::infer_oxygen_kernel<<<(M + 127) / 128, 128, 0, st>>>(bb_out, o_out, B, T);
+        c->launches++;
+    }
+    if (plddt_out) {
+        const int A = c->cfg.n_aux_out;
+        if (launch_gemm(c, gemm::EPI_BIAS_GELU_F32, c->xn, c->p0_w, M, D, D, c->headh, D, c->p0_b, 1.f, st)) return 1;
+        if (launch_layernorm(c, c->headh, c->p2_w, c->p2_b, c->att, M, D, st)) return 1;
+        if (launch_gemm(c, gemm::EPI_BIAS_F32, c->att, c->p3_w, M, A, D, c->aux_ws, A, c->p3_b, 1.f, st)) return 1;
+        dec::plddt_mean_kernel<<<(M + 7) / 8, 256, 0, st>>>(c->aux_ws, A, A, plddt_out, M);
+        c->launches++;
+    }
+    CK(cudaGetLastError());
     return 0;
 }
 

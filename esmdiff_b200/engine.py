@@ -43,8 +43,24 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+@dataclass
+class DecoderDims:
+    """esm ``StructureTokenDecoder(d_model=1280, n_heads=20, n_layers=30)`` (ESM3_structure_decoder_v0):
+    the VQ-VAE decoder behind ``ESM3.decode`` (reference call site slm/sample_esmdiff.py:56-61)."""
+    d_model: int = 1280
+    n_heads: int = 20
+    n_layers: int = 30
+    n_affine_out: int = 9 + 7 * 2          # Dim6RotStructureHead.proj: trans 3, x 3, y 3, 7 torsion sin/cos pairs
+    plddt_bins: int = 50                   # C.VQVAE_PLDDT_BINS; 0 = no pLDDT head
+    struct_vocab: int = 4101               # 4096 codes + 5 special tokens
+
+    @property
+    def ffn_hidden(self) -> int:
+        return int(((8.0 / 3.0 * self.d_model) + 255) // 256 * 256)
+
+
 class Engine:
-    def __init__(self, dims: Dims | None = None, device: int | None = None):
+    def __init__(self, dims: Dims | DecoderDims | None = None, device: int | None = None):
         self.dims = dims or Dims()
         self.L = _lib.lib()
         if not torch.cuda.is_available():
@@ -52,8 +68,12 @@ class Engine:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         d = self.dims
-        cfg = Cfg(d.d_model, d.n_heads, d.n_layers, d.ffn_hidden, d.n_structure_heads, d.seq_vocab,
-                  d.struct_vocab, d.time_freq_dim, int(d.time_conditioning))
+        if isinstance(d, DecoderDims):
+            cfg = Cfg(d.d_model, d.n_heads, d.n_layers, d.ffn_hidden, d.n_affine_out, 0, d.struct_vocab, 0, 0,
+                      1, d.plddt_bins)
+        else:
+            cfg = Cfg(d.d_model, d.n_heads, d.n_layers, d.ffn_hidden, d.n_structure_heads, d.seq_vocab,
+                      d.struct_vocab, d.time_freq_dim, int(d.time_conditioning))
         h = C.c_void_p()
         rc = self.L.esmdiff_create(C.byref(cfg), self.device_index, C.byref(h))
         if rc != 0:
@@ -226,6 +246,19 @@ class Engine:
                                                     int(steps), float(eps), int(seed),
                                                     int(noise_removal), _ptr(out)))
         return out
+
+    def decode_structure(self, structure_tokens, want_affine=False):
+        """Batched VQ-VAE structure decode (engine built from :class:`DecoderDims`).  int64 (B,T)
+        tokens INCLUDING BOS/EOS -> (bb (B,T,3,3) N/CA/C, o (B,T,3), plddt (B,T) | None, affine | None)."""
+        B, T = structure_tokens.shape
+        tok = structure_tokens.to(self.device, torch.int64).contiguous()
+        bb = torch.empty(B, T, 3, 3, dtype=torch.float32, device=self.device)
+        o = torch.empty(B, T, 3, dtype=torch.float32, device=self.device)
+        pl = torch.empty(B, T, dtype=torch.float32, device=self.device) if self.dims.plddt_bins else None
+        aff = torch.empty(B, T, self.dims.n_affine_out, dtype=torch.float32, device=self.device) if want_affine else None
+        self._check(self.L.esmdiff_decode_structure(self.h, _ptr(tok), B, T, _ptr(bb), _ptr(o), _ptr(pl), _ptr(aff),
+                                                    _stream()))
+        return bb, o, pl, aff
 
     # -- single kernels (tests, roofline timing) ----------------------------------------------
     def op_gemm(self, epilogue: int, a, w, out, bias=None, scale=1.0, n=None):

@@ -4,12 +4,18 @@
     --input DIR --ckpt F --output DIR --mode {gibbs,ddpm} --num_steps N --num_samples N --mask_ids a,b,c
 
 Output layout as the reference: ``OUT/step{N}_eps{eps}_N{num}_{time}/{stem}.pdb`` (skipped when it
-exists, :155-160).  The step after "Sampling token time" -- VQ-VAE structure decoding and PDB
-writing (:225-231) -- needs the pretrained ESM3 structure decoder from the ``esm`` package, which
-is outside this path: when ``esm`` is importable it is used exactly as the
-reference uses it; otherwise the sampled structure tokens are written next to where the PDB
-would go (``{stem}.structure_tokens.pt``) and the decode step is reported as skipped.
+exists, :155-160), a multi-MODEL file in ``merge_pdbfiles``' layout.  The step after "Sampling
+token time" -- VQ-VAE structure decoding and PDB writing (:225-231) -- runs BATCHED on the same
+CUDA kernels (esmdiff_b200/decoder.py) when decoder weights are given:
+    --decoder_ckpt PATH     state dict of esm's ``StructureTokenDecoder`` (the file the esm package
+                            fetches as data/weights/esm3_structure_decoder_v0.pth)
+    --decoder_ckpt random   random-init weights of that architecture (plumbing / throughput runs)
+Without it: when the ``esm`` package is importable it is used exactly as the reference uses it
+(serial B=1 decodes); otherwise the sampled structure tokens are written next to where the PDB would
+go (``{stem}.structure_tokens.pt``) and the decode step is reported as skipped.
 ``--mode gibbs`` (the esm SDK's own sampler) is not part of this path and is refused.
+Multi-GPU: ``torchrun --nproc-per-node N -m esmdiff_b200.sample_esmdiff ...`` shards the samples of
+every target over the ranks; rank 0 decodes and writes.
 """
 from __future__ import annotations
 
@@ -20,7 +26,8 @@ from time import strftime, time
 import torch
 
 from .checkpoint_utils import load_state_dict_from_lightning_ckpt
-from .sampling import sample_structure_tokens
+from . import distributed as D
+from .sampling import sample_structure_tokens_sharded
 from .tokenization import sequence_from_pdb, tokenize_sequence
 
 
@@ -61,15 +68,26 @@ def merge_pdbfiles(pdb_files, save_to: Path):
 
 @torch.no_grad()
 def ddpm_sample_by_esm(sequence, pl_model, output_dir: Path, sample_basename: str, num_samples=5,
-                       num_steps=10, eps=1e-5, mask_ids=None, structure_tokens=None, sample_max_t=1.0):
+                       num_steps=10, eps=1e-5, mask_ids=None, structure_tokens=None, sample_max_t=1.0,
+                       rank=0, world=1, seed=None, decoder=None):
+    """reference sample_esmdiff.py:137-233.  ``rank`` / ``world`` (torchrun, one process per GPU):
+    every rank samples its share of ``num_samples``; rank 0 alone decodes and writes."""
     str_time = strftime("%Y%m%d-%H%M%S")
     output_dir = output_dir / f"step{num_steps}_eps{eps}_N{num_samples}_{str_time}"
     save_to = output_dir / f"{sample_basename}.pdb"
-    print(f"Results will save to {save_to}")
-    if save_to.exists():
-        print(f"Skip existing {save_to}")
+    skip = save_to.exists()
+    if world > 1:                      # one decision for all ranks (rank 0's clock and file system view)
+        box = [skip]
+        torch.distributed.broadcast_object_list(box, src=0)
+        skip = box[0]
+    if rank == 0:
+        print(f"Results will save to {save_to}")
+    if skip:
+        if rank == 0:
+            print(f"Skip existing {save_to}")
         return None
-    output_dir.mkdir(parents=True, exist_ok=True)
+    if rank == 0:
+        output_dir.mkdir(parents=True, exist_ok=True)
     if mask_ids is not None:
         assert structure_tokens is not None, \
             "inpainting needs structure tokens of the known residues (VQ-VAE encoder output)"
@@ -80,11 +98,16 @@ def ddpm_sample_by_esm(sequence, pl_model, output_dir: Path, sample_basename: st
         sequence = "".join(seq)
     seq_tokens = tokenize_sequence(sequence)
     start_t = time()
-    tokens, _ = sample_structure_tokens(pl_model, seq_tokens, num_samples, num_steps, eps=eps,
-                                        structure_tokens=structure_tokens, mask_ids=mask_ids,
-                                        sample_max_t=sample_max_t)
+    tokens, _ = sample_structure_tokens_sharded(pl_model, seq_tokens, num_samples, num_steps, rank=rank, world=world,
+                                                seed=seed, eps=eps, structure_tokens=structure_tokens,
+                                                mask_ids=mask_ids, sample_max_t=sample_max_t, verbose=rank == 0)
     tokens = tokens.cpu()
-    if _esm_available():
+    if rank != 0:
+        return tokens
+    if decoder is not None:
+        from .decoder import decode_to_pdb
+        decode_to_pdb(decoder, tokens, "".join(sequence), save_to)
+    elif _esm_available():
         import tempfile
         with tempfile.TemporaryDirectory() as tmp:
             paths = [Path(tmp) / f"{sample_basename}.{i}.pdb" for i in range(len(tokens))]
@@ -107,6 +130,12 @@ def get_argparser():
     p.add_argument("--num_steps", type=int, default=25, help="Number of denoising steps.")
     p.add_argument("--num_samples", type=int, default=10, help="Number of samples to generate.")
     p.add_argument("--mask_ids", type=str, default=None, help="Comma-separated list of masked indices.")
+    p.add_argument("--seed", type=int, default=None,
+                   help="(extension) seed torch before sampling; under torchrun rank r uses seed + its first "
+                        "sample index.  Default: unseeded, as the reference")
+    p.add_argument("--decoder_ckpt", type=str, default=None,
+                   help="(extension) esm StructureTokenDecoder state dict for the built-in batched decode, or "
+                        "'random' for random-init weights of that architecture")
     p.add_argument("--prior_tokens", type=str, default=None,
                    help="(extension) .pt with 'structure_tokens' (L+2,) for --mask_ids inpainting when "
                         "the esm VQ-VAE encoder is not installed")
@@ -119,20 +148,35 @@ def main(argv=None):
         raise SystemExit("esmdiff_b200 implements --mode ddpm only (gibbs is the esm SDK's sampler, "
                          "outside this path)")
     assert args.ckpt is not None, "--mode ddpm needs --ckpt (sample_esmdiff.py:252-258)"
-    model = load_state_dict_from_lightning_ckpt(args.ckpt, device="cuda")
+    # `torchrun --nproc-per-node N -m esmdiff_b200.sample_esmdiff ...`: one process per GPU, the
+    # samples of every target sharded over the ranks; plain `python -m` = one GPU
+    rank, world, local = D.init_from_env()
+    device = f"cuda:{local}" if world > 1 else "cuda"
+    model = load_state_dict_from_lightning_ckpt(args.ckpt, device=device)
     data_path = Path(args.input)
     assert data_path.is_dir(), f"Invalid directory {data_path} (Currently we only support pdb files in a folder as input)."
-    print(f">>> Sampling mode = {args.mode} ...")
+    if rank == 0:
+        print(f">>> Sampling mode = {args.mode} ..." + (f" ({world} GPUs)" if world > 1 else ""))
     output_dir = Path(args.output)
-    output_dir.mkdir(parents=True, exist_ok=True)
+    if rank == 0:
+        output_dir.mkdir(parents=True, exist_ok=True)
+    decoder = None
+    if args.decoder_ckpt and rank == 0:              # rank 0 alone decodes and writes
+        from .decoder import load_decoder
+        decoder = load_decoder(None if args.decoder_ckpt == "random" else args.decoder_ckpt,
+                               device=local if world > 1 else None)
     prior = None
     if args.prior_tokens:
         prior = torch.load(args.prior_tokens, weights_only=False)["structure_tokens"].to(torch.int64)
-    for p in [q for q in data_path.iterdir() if q.suffix == ".pdb"]:
+    for p in sorted(q for q in data_path.iterdir() if q.suffix == ".pdb"):
         sequence = sequence_from_pdb(p)
         mask_ids = [int(i) for i in args.mask_ids.split(",")] if args.mask_ids is not None else None
         ddpm_sample_by_esm(sequence, model, output_dir, p.stem, num_samples=args.num_samples,
-                           num_steps=args.num_steps, mask_ids=mask_ids, structure_tokens=prior)
+                           num_steps=args.num_steps, mask_ids=mask_ids, structure_tokens=prior,
+                           rank=rank, world=world, seed=args.seed, decoder=decoder)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -91,3 +91,32 @@ def sample_structure_tokens(model, sequence_tokens_singleton: torch.Tensor, num_
     if verbose:
         print(f"Sampling token time: {elapsed:.2f}s")
     return tokens, elapsed
+
+
+@torch.no_grad()
+def sample_structure_tokens_sharded(model, sequence_tokens_singleton: torch.Tensor, num_samples: int,
+                                    num_steps: int, rank: int = 0, world: int = 1, seed: int | None = None,
+                                    **kw):
+    """The same job over ``world`` ranks (one process per GPU, torchrun): samples are i.i.d. given the
+    sequence (the reference ``repeat``s one row, sample_esmdiff.py:186,190), so rank r samples its
+    contiguous share ``distributed.shard_samples(num_samples, world, r)`` with no per-step
+    communication and the int64 tokens are all-gathered once at the end.  Every rank
+    returns the full (num_samples, L) tensor and the max-over-ranks window time.
+    RNG contract: ``seed`` given -> each rank seeds torch with ``seed + first_sample_index`` before
+    sampling (identical tokens for any later re-run with the same world size); None -> whatever
+    state the process's generator is in, as in the reference."""
+    from . import distributed as D
+    spans = [D.shard_samples(num_samples, world, r) for r in range(world)]
+    first, count = spans[rank]
+    if seed is not None:
+        torch.manual_seed(int(seed) + first)
+    L = sequence_tokens_singleton.size(0) - 2
+    if count > 0:
+        tokens, elapsed = sample_structure_tokens(model, sequence_tokens_singleton, count, num_steps, **kw)
+    else:
+        dev = getattr(model, "device", "cpu")
+        tokens, elapsed = torch.empty(0, L, dtype=torch.int64, device=dev), 0.0
+    if world > 1:
+        tokens = D.gather_tokens(tokens, [c for _, c in spans])
+        elapsed = D.max_over_ranks(elapsed, tokens.device if tokens.is_cuda else None)
+    return tokens, elapsed

@@ -83,3 +83,48 @@ def random_state_dict(dims: Dims | None = None, device="cuda", seed: int = 0, fu
     sd["sigma_embedder.mlp.2.weight"] = lin(D, D)
     sd["sigma_embedder.mlp.2.bias"] = lin_b(D, D)
     return sd
+
+
+def random_decoder_state_dict(dims=None, device="cuda", seed: int = 0, full: bool = False) -> dict:
+    """Default-initialiser weights of esm's ``StructureTokenDecoder`` (ESM3_structure_decoder_v0
+    dims) under its state-dict key names.  ``full`` adds the pairwise (pTM / PAE) head the path
+    drops."""
+    from .engine import DecoderDims
+    d = dims or DecoderDims()
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    D, F = d.d_model, d.ffn_hidden
+
+    def lin(out_f, in_f):
+        return (torch.rand(out_f, in_f, device=dev, generator=g) * 2 - 1) / math.sqrt(in_f)
+
+    def lin_b(out_f, in_f):
+        return (torch.rand(out_f, device=dev, generator=g) * 2 - 1) / math.sqrt(in_f)
+
+    sd = {"embed.weight": torch.randn(d.struct_vocab, D, device=dev, generator=g)}
+    for l in range(d.n_layers):
+        p = f"decoder_stack.blocks.{l}."
+        sd[p + "attn.layernorm_qkv.0.weight"] = torch.ones(D, device=dev)
+        sd[p + "attn.layernorm_qkv.0.bias"] = torch.zeros(D, device=dev)
+        sd[p + "attn.layernorm_qkv.1.weight"] = lin(3 * D, D)
+        sd[p + "attn.out_proj.weight"] = lin(D, D)
+        sd[p + "attn.q_ln.weight"] = torch.ones(D, device=dev)
+        sd[p + "attn.k_ln.weight"] = torch.ones(D, device=dev)
+        sd[p + "ffn.0.weight"] = torch.ones(D, device=dev)
+        sd[p + "ffn.0.bias"] = torch.zeros(D, device=dev)
+        sd[p + "ffn.1.weight"] = lin(2 * F, D)
+        sd[p + "ffn.3.weight"] = lin(D, F)
+    sd["decoder_stack.norm.weight"] = torch.ones(D, device=dev)
+    a = "affine_output_projection."
+    sd[a + "ffn1.weight"], sd[a + "ffn1.bias"] = lin(D, D), lin_b(D, D)
+    sd[a + "norm.weight"], sd[a + "norm.bias"] = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    sd[a + "proj.weight"], sd[a + "proj.bias"] = lin(d.n_affine_out, D), lin_b(d.n_affine_out, D)
+    if d.plddt_bins:
+        h = "plddt_head."
+        sd[h + "0.weight"], sd[h + "0.bias"] = lin(D, D), lin_b(D, D)
+        sd[h + "2.weight"], sd[h + "2.bias"] = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+        sd[h + "3.weight"], sd[h + "3.bias"] = lin(d.plddt_bins, D), lin_b(d.plddt_bins, D)
+    if full:
+        h = "pairwise_classification_head."
+        sd[h + "linear1.weight"], sd[h + "linear1.bias"] = lin(128, D), lin_b(128, D)
+    return sd

@@ -37,7 +37,13 @@ typedef struct esmdiff_cfg {
     int32_t struct_vocab;       /* 4101 */
     int32_t time_freq_dim;      /* 256, TimestepEmbedder.frequency_embedding_size (net.py:487) */
     int32_t time_conditioning;  /* mdlm.yaml:40; 0 -> sigma is zeroed (model.py:538-539) */
-    int32_t reserved[7];
+    int32_t model_kind;         /* 0: the sampling network above.  1: the VQ-VAE structure token decoder
+                                 * (esm StructureTokenDecoder, ESM3_structure_decoder_v0: d_model 1280, 20 heads,
+                                 * 30 blocks, ffn_hidden 3584, scale_residue=False); then n_structure_heads is
+                                 * the width of Dim6RotStructureHead.proj (23) and struct_vocab the rows of
+                                 * `embed` (4101); seq_vocab, time_* are unused */
+    int32_t n_aux_out;          /* model_kind 1: bins of the pLDDT head (50), 0 = head absent */
+    int32_t reserved[5];
 } esmdiff_cfg;
 
 enum esmdiff_dtype { ESMDIFF_F32 = 0, ESMDIFF_BF16 = 1 };
@@ -112,6 +118,22 @@ int esmdiff_ddpm_sample(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t*
 int esmdiff_ddpm_sample_host(esmdiff_ctx* ctx, const int64_t* seq_host, const int64_t* prior_host,
                              int B, int T, int steps, float eps, uint64_t seed, int noise_removal,
                              int64_t* out_host);
+
+/* Replaces the structure half of esm3_model.decode(prot) (slm/sample_esmdiff.py:56-61 -> esm
+ * ESM3.decode -> StructureTokenDecoder.decode + ProteinChain.infer_oxygen), BATCHED over all samples
+ * instead of the reference's serial B=1 loop (sample_esmdiff.py:225-230).  Context of model_kind 1.
+ *   tokens_dev   : int64 [B*T] structure tokens INCLUDING the BOS (4098) / EOS (4097) positions
+ *   bb_out_dev   : fp32 [B*T, 3, 3]  N, CA, C of every position (rows of BOS/EOS are meaningless)
+ *   o_out_dev    : fp32 [B*T, 3]     inferred carbonyl O (NaN at BOS/EOS and the last residue), or NULL
+ *   plddt_out_dev: fp32 [B*T]        CategoricalMixture mean of the pLDDT head in [0,1], or NULL
+ *   affine_out_dev: fp32 [B*T, n_structure_heads] raw Dim6RotStructureHead.proj output, or NULL
+ * Weight keys: StructureTokenDecoder.state_dict() names ("embed.weight",
+ * "decoder_stack.blocks.0.attn.out_proj.weight", "affine_output_projection.proj.bias",
+ * "plddt_head.3.weight", ...); "pairwise_classification_head.*" (pTM / PAE, not written to the PDB)
+ * is accepted and dropped. */
+int esmdiff_decode_structure(esmdiff_ctx* ctx, const int64_t* tokens_dev, int B, int T,
+                             float* bb_out_dev, float* o_out_dev, float* plddt_out_dev,
+                             float* affine_out_dev, void* stream);
 
 /* Waits for the stream and reports asynchronous failures: CUDA errors, out-of-range token ids
  * (the reference raises IndexError in nn.Embedding), pipeline watchdog trips. */

@@ -135,6 +135,95 @@ def test_config_instantiation_targets():
         assert block["sigma_embedder"]["_target_"] in cu.TARGETS and block["_target_"] in cu.TARGETS
 
 
+COMPOSED_MODEL_YAML = """
+# what hydra writes to <run>/.hydra/config.yaml for `train.py experiment=mdlm`: configs/model/default.yaml
+# with configs/experiment/mdlm.yaml merged on top (dict nodes merge, so default.yaml's optimizer
+# factory and the T5 baseline's net.config survive underneath)
+model:
+  _target_: slm.models.model.MaskedDiffusionLanguageModeling
+  compile: false
+  optimizer:
+    _target_: torch.optim.AdamW
+    _partial_: true
+    lr: 1e-5
+  scheduler: null
+  net:
+    _target_: slm.models.net.CustomizedESM3
+    config:
+      _target_: transformers.T5Config
+      is_decoder: false
+      num_layers: 12
+      vocab_size: 4101
+      d_model: 1024
+    pretrained: true
+    n_structure_heads: 4101
+    n_sequence_heads: 0
+{net_extra}
+  noise_schedule:
+    _target_: slm.utils.noise_utils.LogLinearNoise
+  T: 0
+  noise_removal: false
+  sampling_eps: 1e-3
+  time_conditioning: true
+  change_of_variables: false
+  importance_sampling: false
+  sequence_prediction: false
+  condition_dropout: 0.0
+  condition_mask_rate: 0.0
+  coupled_condition_mask: false
+  structure_only: false
+  sigma_embedder:
+    _target_: slm.models.net.TimestepEmbedder
+    hidden_size: {hidden}
+"""
+
+
+def write_run_dir(root: Path, layout: str, net_extra: str = "", hidden: int = 1536, module=None) -> Path:
+    """A training run directory as lightning + hydra leave it: <run>/.hydra/config.yaml and
+    <run>/checkpoints/<name>; `layout` "file" = one .pt file holding {'module': ...}, "dir" = a
+    DeepSpeed checkpoint directory <name>.ckpt/checkpoint/mp_rank_00_model_states.pt.  Returns the
+    path a user passes as --ckpt."""
+    run = root / "logs" / "train" / "runs" / "2024-01-01_00-00-00"
+    (run / ".hydra").mkdir(parents=True)
+    (run / ".hydra" / "config.yaml").write_text(COMPOSED_MODEL_YAML.format(net_extra=net_extra, hidden=hidden))
+    payload = {"module": module if module is not None else {}}
+    if layout == "file":
+        ckpt = run / "checkpoints" / "last.pt"
+        ckpt.parent.mkdir(parents=True)
+        torch.save(payload, ckpt)
+    else:
+        ckpt = run / "checkpoints" / "epoch_003.ckpt"
+        (ckpt / "checkpoint").mkdir(parents=True)
+        torch.save(payload, ckpt / "checkpoint" / "mp_rank_00_model_states.pt")
+    return ckpt
+
+
+@pytest.mark.parametrize("layout", ["file", "dir"])
+def test_checkpoint_config_discovery_and_composed_config(tmp_path, layout):
+    """reference checkpoint_utils.py:45-56: the run's .hydra/config.yaml sits two levels above the
+    checkpoint for BOTH layouts (the DeepSpeed branch takes four parents of
+    dir/checkpoint/mp_rank_00_model_states.pt); a composed config with the default.yaml optimizer
+    factory and the T5 net.config block must resolve to this package's classes without
+    instantiating either."""
+    from esmdiff_b200 import checkpoint_utils as cu
+    ckpt = write_run_dir(tmp_path, layout)
+    block = cu.load_model_cfg(ckpt)
+    assert block["noise_removal"] is False and block["optimizer"]["_target_"] == "torch.optim.AdamW"     # the run's file, not the default
+    model_kwargs, net_kwargs = cu.split_model_cfg(block)
+    assert net_kwargs == {"pretrained": True, "n_structure_heads": 4101, "n_sequence_heads": 0}
+    assert not set(cu.TRAINING_ONLY_KEYS) & set(model_kwargs) and "net" not in model_kwargs
+    built = cu.instantiate({k: v for k, v in model_kwargs.items() if k != "_target_"})
+    assert type(built["noise_schedule"]).__name__ == "LogLinearNoise" and built["sampling_eps"] == 1e-3
+    assert built["sigma_embedder"].mlp[2].weight.shape == (1536, 1536)
+    with pytest.raises(ValueError):
+        cu.split_model_cfg({"_target_": "slm.models.model.ConditionalLanguageModeling", "net": {}})
+    # no run directory around the checkpoint -> fallback (reference: configs/experiment/mdlm.yaml)
+    lone = tmp_path / "elsewhere" / "x" / "release_v0.pt"
+    lone.parent.mkdir(parents=True)
+    torch.save({"module": {}}, lone)
+    assert cu.load_model_cfg(lone)["noise_removal"] is True
+
+
 def test_timestep_embedder_host_mirror(golden_dir):
     from esmdiff_b200.net import TimestepEmbedder
     g = np.load(golden_dir / "timestep_embedder.npz")
@@ -190,6 +279,23 @@ want = (torch.arange(N)[:, None] * 100 + torch.arange(L)[None]).to(torch.int64)
 assert torch.equal(allt, want), (rank, allt)
 t = torch.tensor([float(rank + 1)])
 assert D.max_over_ranks(t.item()) == 2.0
+# the sharded sampling driver (sample_esmdiff's torchrun path) with a stand-in sampler: rank r draws
+# its share after seeding with seed + first sample index; every rank ends with the full job
+from esmdiff_b200.sampling import sample_structure_tokens_sharded, chunk_sizes
+class FakeModel:
+    rng, device = "torch", "cpu"
+    def ddpm_sample(self, num_steps, sequence_tokens, eps, input_prior, sample_max_t):
+        return torch.randint(0, 4096, sequence_tokens.shape)
+seq = torch.tensor([0, 5, 6, 7, 8, 9, 2])
+tok, _ = sample_structure_tokens_sharded(FakeModel(), seq, 5, 3, rank=rank, world=world, seed=40, verbose=False)
+want = []
+for r in range(world):
+    first, count = D.shard_samples(5, world, r)
+    torch.manual_seed(40 + first)
+    want.append(torch.cat([torch.randint(0, 4096, (b, 7)) for b in chunk_sizes(7, count)])[:, 1:-1])
+assert torch.equal(tok, torch.cat(want)) and tok.shape == (5, 5), (rank, tok)
+none, _ = sample_structure_tokens_sharded(FakeModel(), seq, 1, 3, rank=rank, world=world, seed=1, verbose=False)
+assert none.shape == (1, 5)                       # rank 1 owns no sample of a 1-sample job
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)

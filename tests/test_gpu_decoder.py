@@ -1,0 +1,138 @@
+"""GPU: SURVEY.md 8f row 1 -- batched VQ-VAE structure decode + PDB writing, and the CLI end to end
+(reference slm/sample_esmdiff.py:41-61, 137-233, 249-294; checkpoint_utils.py:41-74).
+
+The decoder's arithmetic is esm==3.0.4's (not vendored, weights not available offline): the fp32
+oracle oracle/vqvae_ref.py is a restatement, PARITY UNPINNED.  Bounds: the Dim6RotStructureHead
+output (23 floats per token) like the sampling network's logits (<= 2x measured bf16 noise vs the
+fp32 oracle, drift floor vs the bf16-emulating oracle); the row kernels that turn it into
+coordinates against the oracle's own functions applied to the SAME head output (fp32: 1e-4 A).
+"""
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import esm3_ref, vqvae_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BPTI = "RPDFCLEPPYTGPCKARIIRYFYNAKAGLCQTFVYGGCRAKRNNFKSAEDCMRTCGGA"
+
+
+def rel_fro(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
+def _tokens(B, T, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.randint(0, 4096, (B, T), generator=g)
+    tok[:, 0], tok[:, -1] = 4098, 4097
+    tok[0, 3] = 4096                                   # specials are legal inputs (not shielded by the sampler)
+    return tok
+
+
+@pytest.mark.parametrize("name,dims,B,T", [("tiny", dict(d_model=256, n_heads=4, n_layers=2), 3, 70),
+                                           ("esm3_decoder_v0", dict(), 2, 60),
+                                           ("esm3_decoder_v0_T258", dict(), 1, 258)])
+def test_decode_structure_vs_oracles(name, dims, B, T):
+    from esmdiff_b200.engine import DecoderDims, Engine
+    from esmdiff_b200.synthetic import random_decoder_state_dict
+    dd = DecoderDims(**dims)
+    sd = random_decoder_state_dict(dd, device=DEV, seed=1, full=True)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    for k in sd:                                       # non-trivial LayerNorm weights / biases
+        if k.endswith(("layernorm_qkv.0.weight", "ffn.0.weight", "q_ln.weight", "k_ln.weight", "norm.weight", "2.weight")):
+            sd[k] = sd[k] * (1 + 0.2 * torch.randn(sd[k].shape, device=DEV, generator=g))
+        elif k.endswith(("layernorm_qkv.0.bias", "ffn.0.bias", "norm.bias", "2.bias")):
+            sd[k] = sd[k] + 0.1 * torch.randn(sd[k].shape, device=DEV, generator=g)
+    eng = Engine(dd)
+    eng.load_state_dict(sd)
+    ref = vqvae_ref.build_decoder_from_state_dict(
+        vqvae_ref.DecoderDimsRef(d_model=dd.d_model, n_heads=dd.n_heads, n_layers=dd.n_layers), sd)
+    tok = _tokens(B, T)
+    want = ref.decode(tok)
+    emu = vqvae_ref.decode_emulated(ref, tok)
+    bb, o, plddt, aff = eng.decode_structure(tok, want_affine=True)
+    eng.synchronize()
+    bb, o, plddt, aff = bb.cpu(), o.cpu(), plddt.cpu(), aff.cpu()
+    res = {"affine_rel_fp32": rel_fro(aff, want["affine"]), "affine_rel_emul": rel_fro(aff, emu["affine"]),
+           "bb_maxabs_fp32_A": float((bb - want["bb_pred"]).abs().max()),
+           "bb_maxabs_emul_A": float((bb - emu["bb_pred"]).abs().max()),
+           "plddt_maxabs_fp32": float((plddt - want["plddt"]).abs().max())}
+    # row kernels in isolation: the oracle's functions on the library's own head output
+    bb_own = vqvae_ref.frames_to_backbone(aff)
+    res["frames_kernel_maxabs_A"] = float((bb - bb_own).abs().max())
+    o_own = torch.full_like(o, float("nan"))
+    o_own[:, 1:-1] = vqvae_ref.infer_oxygen(bb[:, 1:-1])
+    assert torch.equal(torch.isnan(o), torch.isnan(o_own)) and int(torch.isnan(o[:, 1:-2]).sum()) == 0
+    res["oxygen_kernel_maxabs_A"] = float((o - o_own)[:, 1:-2].abs().max())
+    print(f"\n[decoder {name} B={B} T={T}] " + ", ".join(f"{k} {v:.2e}" for k, v in res.items()))
+    assert res["frames_kernel_maxabs_A"] < 1e-3 and res["oxygen_kernel_maxabs_A"] < 1e-3
+    assert res["affine_rel_fp32"] < 9e-3 and res["affine_rel_emul"] < 7e-3
+    assert res["bb_maxabs_fp32_A"] < 0.5 and res["plddt_maxabs_fp32"] < 2e-2
+    # geometry the head guarantees whatever the weights: ideal N-CA and CA-C bond lengths
+    assert float(((bb[..., 0, :] - bb[..., 1, :]).norm(dim=-1) - 1.4592).abs().max()) < 1e-3
+    assert float(((bb[..., 2, :] - bb[..., 1, :]).norm(dim=-1) - 1.5251).abs().max()) < 1e-3
+    assert float(((o - bb[..., 2, :])[:, 1:-2].norm(dim=-1) - 1.2311).abs().max()) < 1e-3     # |O_VECTOR|
+    eng.close()
+
+
+def _write_pdb(path, seq):
+    three = {v: k for k, v in __import__("esmdiff_b200.tokenization", fromlist=["x"]).THREE_TO_ONE.items() if k != "MSE"}
+    lines = [f"ATOM  {i + 1:5d}  CA  {three[a]:>3s} A{i + 1:4d}    {i * 3.8:8.3f}{0.0:8.3f}{0.0:8.3f}  1.00  0.00           C  "
+             for i, a in enumerate(seq)]
+    path.write_text("\n".join(lines) + "\nEND\n")
+
+
+def test_cli_end_to_end_with_deepspeed_checkpoint(tmp_path, capsys):
+    """sample_esmdiff.main on data/targets/bpti-like input with a DeepSpeed-layout checkpoint
+    (tiny dims, composed hydra config incl. the training-only blocks) and the built-in decoder:
+    checkpoint discovery + loading (checkpoint_utils.py:41-74), the chunked sampling loop
+    (sample_esmdiff.py:177-223), batched decode + multi-MODEL PDB (:225-231).  The file must equal,
+    byte for byte, what the same pieces give when driven by hand under the same seed."""
+    from conftest import TINY
+    from test_abi_and_host import write_run_dir
+    from esmdiff_b200 import sample_esmdiff
+    from esmdiff_b200.checkpoint_utils import load_state_dict_from_lightning_ckpt
+    from esmdiff_b200.decoder import decode_to_pdb, load_decoder
+    from esmdiff_b200.sampling import sample_structure_tokens
+    from esmdiff_b200.tokenization import sequence_from_pdb, tokenize_sequence
+    net, emb = esm3_ref.build_reference_model(esm3_ref.Esm3Dims(**TINY), seed=5)
+    sd = esm3_ref.full_state_dict(net, emb)
+    extra = "\n".join(f"    {k}: {v}" for k, v in TINY.items())
+    ckpt = write_run_dir(tmp_path / "run", "dir", net_extra=extra, hidden=TINY["d_model"], module=sd)
+    inp = tmp_path / "targets" / "bpti"
+    inp.mkdir(parents=True)
+    _write_pdb(inp / "bpti.pdb", BPTI)
+    assert sequence_from_pdb(inp / "bpti.pdb") == BPTI
+    out = tmp_path / "out"
+    sample_esmdiff.main(["--input", str(inp), "--ckpt", str(ckpt), "--output", str(out), "--mode", "ddpm",
+                         "--num_steps", "6", "--num_samples", "5", "--seed", "7", "--decoder_ckpt", "random"])
+    text = capsys.readouterr().out
+    assert "Loaded experiment config" in text and ".hydra/config.yaml" in text        # the RUN's config was found
+    assert "Sampling token time" in text and "Total time" in text
+    files = list(out.glob("step6_eps1e-05_N5_*/bpti.pdb"))
+    assert len(files) == 1
+    pdb = files[0].read_text()
+    assert pdb.count("MODEL ") == 5 and pdb.count("ENDMDL") == 5 and pdb.rstrip().endswith("END")
+    assert all(len(ln) == 80 for ln in pdb.splitlines())
+    atoms = [ln for ln in pdb.splitlines() if ln.startswith("ATOM")]
+    assert len(atoms) == 5 * (58 * 4 - 1)                                              # no O on the last residue
+    xyz = np.array([[float(ln[30:38]), float(ln[38:46]), float(ln[46:54])] for ln in atoms])
+    assert np.isfinite(xyz).all() and atoms[0][17:20] == "ARG" and atoms[0][12:16] == " N  "
+    # by hand: same checkpoint, same seed, same decoder seed
+    model = load_state_dict_from_lightning_ckpt(ckpt, device="cuda")
+    assert model.noise_removal is True                # forced although the run's config says false (checkpoint_utils.py:71)
+    torch.manual_seed(7)
+    tokens, _ = sample_structure_tokens(model, tokenize_sequence(BPTI), 5, 6, verbose=False)
+    decode_to_pdb(load_decoder(None), tokens.cpu(), BPTI, tmp_path / "hand.pdb")
+    assert (tmp_path / "hand.pdb").read_text() == pdb
+    # single-file checkpoint layout loads the same weights
+    ckpt2 = write_run_dir(tmp_path / "run2", "file", net_extra=extra, hidden=TINY["d_model"], module=sd)
+    model2 = load_state_dict_from_lightning_ckpt(ckpt2, device="cuda")
+    torch.manual_seed(7)
+    tokens2, _ = sample_structure_tokens(model2, tokenize_sequence(BPTI), 5, 6, verbose=False)
+    assert torch.equal(tokens2, tokens)
+    # skip-if-exists (sample_esmdiff.py:158-160) is keyed on the time-stamped directory: a second run writes a new one
+    assert re.search(r"Results will save to .*bpti\.pdb", text)
