@@ -328,11 +328,23 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             // row of the 64-row tile; the eight 16-byte chunks of a row are visited in a lane-rotated
             // order so that the 8 lanes of a quarter warp (rows 128 bytes apart) hit different banks
             const int tr = threadIdx.x - 6 * 32;
-            for (int j = 0; j < nkv; ++j) {
+            // all statistics first (independent loads, one memory latency for the whole K), then tile by
+            // tile as the TMA loads land: the first S MMA waits for tile 0 only
+            float rks[MAX_KV_TILES];
+#pragma unroll
+            for (int j = 0; j < MAX_KV_TILES; ++j) {
                 const int t = j * BKV + tr;
-                const bool live = t < p.T;
-                float rk = 0.f;
-                if (live) rk = row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan + p.nspan, p.nspan, p.ln_eps);
+                rks[j] = (j < nkv && t < p.T)
+                             ? row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan + p.nspan, p.nspan, p.ln_eps)
+                             : 0.f;
+            }
+#pragma unroll 1
+            for (int j = 0; j < nkv; ++j) {
+                const bool live = j * BKV + tr < p.T;
+                float rk = rks[0];                     // select, not index: rks stays in registers
+#pragma unroll
+                for (int k = 1; k < MAX_KV_TILES; ++k)
+                    if (j == k) rk = rks[k];
                 mbar_wait(&k_full[j], 0);
                 if (live) {
                     uint8_t* rowp = sK + j * KV_TILE_BYTES + tr * 128;
@@ -368,6 +380,15 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         const uint32_t t_o = tmem_base + lane_addr + COL_O;
         float sc = p.scale_log2;              // per query row once q_ln's 1/std is folded in (set per query tile)
         float thresh = RESCALE_LOG2 / sc;
+        constexpr int MAX_Q_TILES = (MAX_KV_TILES * BKV + BQ - 1) / BQ;
+        float rqs[MAX_Q_TILES];               // 1/std of this thread's query row in every query tile, fetched up front
+#pragma unroll
+        for (int qt = 0; qt < MAX_Q_TILES; ++qt) {
+            const int t = qt * BQ + r;
+            rqs[qt] = (fused_ln && qt < nq && t < p.T)
+                          ? row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan, p.nspan, p.ln_eps)
+                          : 1.0f;
+        }
 
         // out[row] = O / l for query tile qt (after its last PV has retired), then free O
         auto epilogue = [&](int qt, float l) {
@@ -400,6 +421,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
 
         float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
         float l_run = 0.f, l_prev = 0.f;      // running row sum (relative to m_run); previous tile's final sum
+#pragma unroll 1
         for (int qt = 0; qt < nq; ++qt) {
             const bool active = qt * BQ + warp * 32 < p.T;           // warp-uniform
             for (int j = 0; j < nkv; ++j) {
@@ -409,9 +431,10 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                     l_prev = l_run;
                     l_run = 0.f;
                     if (fused_ln) {
-                        const int t = qt * BQ + r;
-                        const float rq = t < p.T ? row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan,
-                                                            p.nspan, p.ln_eps) : 1.0f;
+                        float rq = rqs[0];                 // select, not index: rqs stays in registers
+#pragma unroll
+                        for (int k = 1; k < MAX_Q_TILES; ++k)
+                            if (qt == k) rq = rqs[k];
                         sc = p.scale_log2 * rq;
                         thresh = RESCALE_LOG2 / sc;
                     }
@@ -440,8 +463,14 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                                 }
                             }
                     } else {
+                        // four independent FMNMX3 chains of 8 (a single 64-deep chain is 64 x 4 clk of latency)
+                        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-                        for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(s[e]));
+                        for (int e = 0; e < 64; e += 8)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                m4[k] = fmax3(m4[k], __uint_as_float(s[e + 2 * k]), __uint_as_float(s[e + 2 * k + 1]));
+                        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                     }
                     if (j == 0) {
                         m_run = mx;
@@ -478,10 +507,10 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                             uint32_t pk[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
-                                const float p0 = fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e]), sc, nm));
-                                const float p1 = fast_exp2(fmaf(__uint_as_float(s[c * 16 + 2 * e + 1]), sc, nm));
-                                rs0 += p0;
-                                rs1 += p1;
+                                float a0, a1;
+                                ffma2(a0, a1, __uint_as_float(s[c * 16 + 2 * e]), __uint_as_float(s[c * 16 + 2 * e + 1]), sc, sc, nm, nm);
+                                const float p0 = fast_exp2(a0), p1 = fast_exp2(a1);
+                                fadd2(rs0, rs1, rs0, rs1, p0, p1);
                                 pk[e] = pack_bf16x2(p0, p1);
                             }
                             tmem_st_32x32b_x8(t_s + c * 8, pk);      // P over the S buffer: 2 bf16 per column

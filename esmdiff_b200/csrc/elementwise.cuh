@@ -317,6 +317,10 @@ __global__ void column_mean_kernel(const float* __restrict__ src, float* __restr
 
 // LayerNorm folded into the following Linear (gemm.cuh, *_LN epilogues), one warp per output row n:
 //   w[n, k]    = W[src(n), k] - colmean[n / center_block][k]   for n < center_rows (else W[src(n), k])
+//                for those rows src(n) also interleaves the rotary partners of every 64-wide head:
+//                position p of a head holds feature (p >> 1) + 32 (p & 1), i.e. (d, d + 32) adjacent,
+//                so that an epilogue thread finds both halves of a rotation in consecutive registers.
+//                q and k get the SAME permutation, which leaves every q.k dot product unchanged.
 //   dst[n, k]  = bf16(w[n, k] * gamma[k])
 //   colsum[n]  = sum_k float(dst[n, k])          (of the ROUNDED weights: it multiplies the row mean)
 //   bias[n]    = sum_k beta[k] * w[n, k]         (fp32; beta may be null)
@@ -336,6 +340,10 @@ fold_layernorm_weight_kernel(const float* __restrict__ src, const float* __restr
         sr = within < 128 ? blk * 128 + within : swiglu_hidden + blk * 128 + (within - 128);
     }
     const float* cm = (colmean != nullptr && r < center_rows) ? colmean + (r / center_block) * cols : nullptr;
+    if (r < center_rows) {
+        const long long within = r % 64;
+        sr = r - within + (within >> 1) + 32 * (within & 1);
+    }
     float cs = 0.f, bs = 0.f;
     for (long long k = lane; k < cols; k += 32) {
         float w = src[sr * cols + k];
@@ -351,6 +359,14 @@ fold_layernorm_weight_kernel(const float* __restrict__ src, const float* __restr
         colsum[r] = cs;
         bias[r] = bs;
     }
+}
+
+// dst[p] = src[rotary-partner interleave of p] per 64-wide head (see fold_layernorm_weight_kernel).
+__global__ void interleave_rotary_pairs_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int within = i % 64;
+    dst[i] = src[i - within + (within >> 1) + 32 * (within & 1)];
 }
 
 // fp32 -> bf16 weight conversion with an optional row permutation (SwiGLU gate/up interleave).

@@ -977,8 +977,8 @@ int esmdiff_finalize_weights(esmdiff_ctx* c) {
     }
     if (c->qk_fused)
         for (LayerW& w : c->layers) {            // q_ln / k_ln weights can be replaced without refolding
-            CK(cudaMemcpy(w.qk_gamma, w.qln_w, D * sizeof(float), cudaMemcpyDeviceToDevice));
-            CK(cudaMemcpy(w.qk_gamma + D, w.kln_w, D * sizeof(float), cudaMemcpyDeviceToDevice));
+            ew::interleave_rotary_pairs_kernel<<<(D + 255) / 256, 256>>>(w.qln_w, w.qk_gamma, D);
+            ew::interleave_rotary_pairs_kernel<<<(D + 255) / 256, 256>>>(w.kln_w, w.qk_gamma + D, D);
         }
     if (c->cfg.model_kind == 0)
         ew::default_tracks_kernel<<<(D + 127) / 128, 128>>>(c->plddt_w, c->plddt_b, c->res_w, c->res_b, c->ss8,

@@ -29,7 +29,10 @@
 //                       RoPE per 64-wide head).  The q and k rows of W are CENTRED offline (column
 //                       means over the 1536 q / k output features removed: q - mean(q) is linear in
 //                       the input), so the epilogue holds y = q - mean(q) in fp32.  It writes
-//                       rope(gamma * y) as bf16 and the per-row sum of y^2 over its 128 columns;
+//                       rope(gamma * y) as bf16 -- with the two halves (d, d + 32) of every rotation
+//                       stored ADJACENT inside their head, a permutation applied to q and k alike
+//                       (folded into the weight rows) that no q.k dot product can see -- and the
+//                       per-row sum of y^2 over its 128 columns;
 //                       the 1/sqrt(mean y^2 + eps) factor is a per-row scalar that commutes with
 //                       the rotation and is applied inside the attention kernel (query rows: in
 //                       the softmax scale; key rows: on the shared-memory K tile).  Statistics
@@ -509,43 +512,43 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         }
                     }
                 } else if constexpr (ROPE) {
-                    // one 64-wide head per staging box: columns d and d + 32 of a head are rotated
-                    // together, 8 rotary frequencies at a time
+                    // the q / k rows of W are stored with the two halves of every rotation adjacent
+                    // (feature d at position 2 d', d + 32 at 2 d' + 1 of its head), so consecutive
+                    // accumulator columns (2 e, 2 e + 1) of a 32-column chunk are one rotary pair with
+                    // frequency index 16 hh + e
                     float sq = 0.f;
 #pragma unroll 1
                     for (int c = 0; c < (BN / 2) / 64; ++c) {
                         if (lane == 0) bulk_wait_group_read<0>();
                         __syncwarp();
 #pragma unroll
-                        for (int g8 = 0; g8 < 4; ++g8) {
-                            uint32_t va[8], vb[8];
-                            float ca[8], ba[8], ga[8], cb[8], bb[8], gb[8];
-                            const int na = n0 + c * 64 + g8 * 8;
-                            tmem_ld8(t_row + c * 64 + g8 * 8, va);
-                            tmem_ld8(t_row + c * 64 + 32 + g8 * 8, vb);
-                            ld_uniform<8>(ca, p.colsum + na);
-                            ld_uniform<8>(ba, p.bias + na);
-                            ld_uniform<8>(ga, p.qk_gamma + na);
-                            ld_uniform<8>(cb, p.colsum + na + 32);
-                            ld_uniform<8>(bb, p.bias + na + 32);
-                            ld_uniform<8>(gb, p.qk_gamma + na + 32);
+                        for (int hh = 0; hh < 2; ++hh) {
+                            uint32_t v[32];
+                            const int na = n0 + c * 64 + hh * 32;
+                            tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
                             tmem_ld_wait();
-                            float oa[8], ob[8];
+                            uint32_t o[16];
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float ya = fmaf(__uint_as_float(va[e]), rstd, fmaf(nrm, ca[e], ba[e]));
-                                const float yb = fmaf(__uint_as_float(vb[e]), rstd, fmaf(nrm, cb[e], bb[e]));
-                                sq = fmaf(ya, ya, sq);
-                                sq = fmaf(yb, yb, sq);
-                                const float za = ya * ga[e], zb = yb * gb[e];
-                                const float cc = rcos[g8 * 8 + e], ss = rsin[g8 * 8 + e];
-                                oa[e] = fmaf(za, cc, -(zb * ss));         // x1 cos - x2 sin
-                                ob[e] = fmaf(zb, cc, za * ss);            // x2 cos + x1 sin
+                            for (int h2 = 0; h2 < 2; ++h2) {               // 16 columns = 8 rotary pairs at a time
+                                float cs[16], bs[16], gs[16];
+                                ld_uniform<16>(cs, p.colsum + na + h2 * 16);
+                                ld_uniform<16>(bs, p.bias + na + h2 * 16);
+                                ld_uniform<16>(gs, p.qk_gamma + na + h2 * 16);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int i = h2 * 16 + 2 * e;
+                                    const float ya = fmaf(__uint_as_float(v[i]), rstd, fmaf(nrm, cs[2 * e], bs[2 * e]));
+                                    const float yb = fmaf(__uint_as_float(v[i + 1]), rstd, fmaf(nrm, cs[2 * e + 1], bs[2 * e + 1]));
+                                    sq = fmaf(ya, ya, sq);
+                                    sq = fmaf(yb, yb, sq);
+                                    const float za = ya * gs[2 * e], zb = yb * gs[2 * e + 1];
+                                    const float cc = rcos[hh * 16 + h2 * 8 + e], ss = rsin[hh * 16 + h2 * 8 + e];
+                                    o[h2 * 8 + e] = pack_bf16x2(fmaf(za, cc, -(zb * ss)),      // x1 cos - x2 sin
+                                                                fmaf(zb, cc, za * ss));        // x2 cos + x1 sin
+                                }
                             }
-                            st_swz16(box, lane, g8, pack_bf16x2(oa[0], oa[1]), pack_bf16x2(oa[2], oa[3]),
-                                     pack_bf16x2(oa[4], oa[5]), pack_bf16x2(oa[6], oa[7]));
-                            st_swz16(box, lane, 4 + g8, pack_bf16x2(ob[0], ob[1]), pack_bf16x2(ob[2], ob[3]),
-                                     pack_bf16x2(ob[4], ob[5]), pack_bf16x2(ob[6], ob[7]));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) st_swz16(box, lane, hh * 4 + j, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                         }
                         fence_proxy_async_smem();
                         __syncwarp();

@@ -268,8 +268,10 @@ def test_qkv_epilogue_with_qk_layernorm_and_rope(engine, B, T, D):
     wc = w.clone()
     wc[:D] -= wc[:D].mean(0, keepdim=True)
     wc[D:2 * D] -= wc[D:2 * D].mean(0, keepdim=True)
-    assert rel_fro(wf, wc * gamma) < 3e-3
-    qkv, sumsq = engine.op_gemm_qkv_rope(xb, wf, bs, stats, cs, torch.cat([qw, kw]).contiguous(), T, 2 * D)
+    pair = lambda z: torch.cat([z[:2 * D].view(2 * H, 2, 32, D).transpose(1, 2).reshape(2 * D, D), z[2 * D:]])
+    assert rel_fro(wf, pair(wc * gamma)) < 3e-3                     # centred, gamma folded, partners interleaved
+    gam = torch.cat([qw, kw]).view(2 * H, 2, 32).transpose(1, 2).reshape(2 * D).contiguous()
+    qkv, sumsq = engine.op_gemm_qkv_rope(xb, wf, bs, stats, cs, gam, T, 2 * D)
     engine.synchronize()
     # torch reference, fp32 throughout
     y = F.layer_norm(x, (D,), gamma, beta, 1e-5) @ w.T
@@ -286,8 +288,10 @@ def test_qkv_epilogue_with_qk_layernorm_and_rope(engine, B, T, D):
     assert float(((got_k - ssq_k).abs() / ssq_k).max()) < 5e-3
     rq = torch.rsqrt(got_q / D + 1e-5)[:, None]
     rk = torch.rsqrt(got_k / D + 1e-5)[:, None]
-    check(qkv[:, :D].float() * rq, qr, 6e-3, 3e-2)
-    check(qkv[:, D:2 * D].float() * rk, kr, 6e-3, 3e-2)
+    # q', k' are stored with the rotary partners (d, d + 32) of every head adjacent: undo for the comparison
+    unpair = lambda z: z.view(M, H, 32, 2).transpose(-1, -2).reshape(M, D)
+    check(unpair(qkv[:, :D].float() * rq), qr, 6e-3, 3e-2)
+    check(unpair(qkv[:, D:2 * D].float() * rk), kr, 6e-3, 3e-2)
     check(qkv[:, 2 * D:], v, 6e-3, 3e-2)
     att = engine.op_attention(qkv, B, T, H, qk_sumsq=sumsq)
     engine.synchronize()

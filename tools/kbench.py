@@ -128,11 +128,43 @@ def bench_rows(flush):
     e.close()
 
 
+def bench_qk(flush):
+    """q_ln / k_ln + RoPE folded into the QKV epilogue + attention (default) against the stand-alone
+    kernel chain (LN-folded store epilogue -> qk_layernorm_rope -> attention), kernel by kernel."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    e = engine()
+    D, H = 1536, 24
+    for (B, T) in [(100, 258), (13, 258), (32, 514)]:
+        M = B * T
+        x = torch.randn(M, D, device=dev, generator=g)
+        xs = x.view(M, D // 128, 128)
+        stats = torch.stack([xs.mean(-1), ((xs - xs.mean(-1, keepdim=True)) ** 2).sum(-1)], -1).contiguous()
+        xb = x.bfloat16()
+        w = torch.randn(3 * D, D, device=dev, generator=g) / D ** 0.5
+        ones = torch.ones(D, device=dev)
+        wf, cs, bs = e.op_fold_layernorm(w, ones, None)
+        wfc, csc, bsc = e.op_fold_layernorm(w, ones, None, center_rows=2 * D, center_block=D)
+        qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=dev)
+        gam = torch.ones(2 * D, device=dev)
+        t_plain = timeit(lambda: e.op_gemm_ln(5, xb, wf, qkv, bias=bs, stats_in=stats, colsum=cs), flush=flush)
+        t_rope = timeit(lambda: e.op_gemm_qkv_rope(xb, wfc, bsc, stats, csc, gam, T, 2 * D), flush=flush)
+        t_row = timeit(lambda: e.op_qk_norm_rope(qkv, ones, ones, B, T), flush=flush)
+        qkv2, sumsq = e.op_gemm_qkv_rope(xb, wfc, bsc, stats, csc, gam, T, 2 * D)
+        t_att = timeit(lambda: e.op_attention(qkv, B, T, H), flush=flush)
+        t_att_ln = timeit(lambda: e.op_attention(qkv2, B, T, H, qk_sumsq=sumsq), flush=flush)
+        fl = 2.0 * M * 3 * D * D
+        print(f"  B={B} T={T}: qkv gemm plain {t_plain * 1e3:.1f} us ({fl / t_plain / 1e9:.0f} TF) | +rope epilogue "
+              f"{t_rope * 1e3:.1f} us ({fl / t_rope / 1e9:.0f} TF) | qk_norm_rope kernel {t_row * 1e3:.1f} us | attention "
+              f"{t_att * 1e3:.1f} us | attention+rstd {t_att_ln * 1e3:.1f} us || chain separate "
+              f"{(t_plain + t_row + t_att) * 1e3:.1f} us, fused {(t_rope + t_att_ln) * 1e3:.1f} us", flush=True)
+    e.close()
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     which = sys.argv[1:] or ["attn", "gemm", "rows"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
-    table = dict(gemm=bench_gemm, attn=bench_attn, rows=bench_rows)
+    table = dict(gemm=bench_gemm, attn=bench_attn, rows=bench_rows, qk=bench_qk)
     for wname in which:
         print(f"=== {wname} ===", flush=True)
         table[wname](flush)
