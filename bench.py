@@ -253,7 +253,11 @@ def gpu_bench(args):
                                             time_conditioning=True, noise_removal=True, rng=args.rng)
     # the job's samples owned by this rank: a contiguous share (strong) or all of them (weak replicas)
     strong = args.scaling == "strong"
-    if strong:
+    if args.shard_of > 1:
+        # one-GPU study of the strong-scaling shard: rank 0's share of an args.shard_of-way split, alone
+        assert world == 1, "--shard-of is a single-GPU projection"
+        shards = [D.shard_samples(n_samples, args.shard_of, 0)]
+    elif strong:
         shards = [D.shard_samples(n_samples, world, r) for r in range(world)]
     else:
         shards = [(0, n_samples)] * world
@@ -377,7 +381,11 @@ def gpu_bench(args):
                         "api": "esmdiff_b200.sampling.sample_structure_tokens (pinned host tokens in, host "
                                "int64 tokens out), uniforms=" + args.rng},
                 "gpu_launches": int(launches), "roofline": roofline}
-        if world == 1 and not args.no_cpu_baseline:
+        if args.shard_of > 1:
+            line["projection"] = (f"rank 0's shard ({count} samples) of a {args.shard_of}-GPU strong-scaling run, measured "
+                                  f"alone on one GPU; x{args.shard_of} = {round(value * n_samples / count, 1)} tokens/s if every "
+                                  "rank took this long")
+        if world == 1 and not args.no_cpu_baseline and args.shard_of <= 1:
             line["cpu_baseline"] = cpu_reference(wl, 3, 1, 24.0, emit_line=False)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -402,6 +410,8 @@ def main():
                     help="N > 1: strong = shard the ONE job's samples over the ranks (default); weak = every "
                          "rank runs the whole job (replicas)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-of", type=int, default=1,
+                    help="(study) run only rank 0's share of an N-way strong-scaling split on ONE GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

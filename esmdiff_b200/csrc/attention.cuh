@@ -81,6 +81,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
     const int q0 = qt * BQ;                     // first query position of this tile
     const int nkv = (p.T + BKV - 1) / BKV;
     const bool fused_ln = p.qk_sumsq != nullptr;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (fused_ln) {
         for (int t = threadIdx.x; t < nkv * BKV; t += THREADS) {

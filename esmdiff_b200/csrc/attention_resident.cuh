@@ -229,6 +229,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    if (warp != 5) pdl_wait();             // every role but the MMA issuer touches global memory
 
     if (warp == 4) {
         // ===================== TMA producer =====================

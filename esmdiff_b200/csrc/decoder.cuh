@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256)
 embed_tokens_kernel(const long long* __restrict__ tok, const float* __restrict__ table, float* __restrict__ x,
                     __nv_bfloat16* __restrict__ xb, float2* __restrict__ stats, int M, int D, int vocab,
                     int* __restrict__ err) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 layernorm_f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                              const float* __restrict__ b, __nv_bfloat16* __restrict__ y, int M,
                              int D, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32, 4)
 qk_layernorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ q_w,
                          const float* __restrict__ k_w, const float* __restrict__ cos_t,
                          const float* __restrict__ sin_t, int M, int D, int T, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -204,6 +208,8 @@ embed_kernel(const long long* __restrict__ seq, const long long* __restrict__ xt
              long long aux_row_stride, float* __restrict__ x, int M, int D, int seq_vocab,
              int struct_vocab, int* __restrict__ err, __nv_bfloat16* __restrict__ xb,
              float2* __restrict__ stats) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -266,6 +272,8 @@ __global__ void default_tracks_kernel(const float* __restrict__ plddt_w, const f
 __global__ void __launch_bounds__(256)
 time_embed_hidden_kernel(float sigma, const float* __restrict__ w0, const float* __restrict__ b0,
                          float* __restrict__ hidden, int D, int F) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= D) return;
@@ -287,6 +295,8 @@ time_embed_hidden_kernel(float sigma, const float* __restrict__ w0, const float*
 __global__ void __launch_bounds__(256)
 time_embed_out_kernel(const float* __restrict__ hidden, const float* __restrict__ w2,
                       const float* __restrict__ b2, float* __restrict__ cond, int D) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (j >= D) return;

@@ -36,6 +36,23 @@ static std::string g_create_error;
         }                                                                                      \
     } while (0)
 
+// Launch with programmatic stream serialization (ptx.cuh): only for kernels that call pdl_wait().
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct LayerW {
     float *ln1_w = nullptr, *ln1_b = nullptr, *qln_w = nullptr, *kln_w = nullptr;
     float *ln2_w = nullptr, *ln2_b = nullptr;
@@ -62,6 +79,7 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    bool pdl = true;           // programmatic dependent launch between the kernels of a forward; ESMDIFF_PDL=0 -> off
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
     // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: tracked per context, not per process
@@ -274,7 +292,8 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
                                     gemm::Cfg<E, BNV>::SMEM_BYTES));                           \
             c->smem_attr_set.insert(fn_);                                                      \
         }                                                                                      \
-        gemm::gemm_bf16_tn_kernel<E, BNV><<<grid, gemm::THREADS, gemm::Cfg<E, BNV>::SMEM_BYTES, st>>>(ta, tb, tc, p); \
+        CK(launch_pdl(c->pdl, gemm::gemm_bf16_tn_kernel<E, BNV>, dim3(grid), dim3(gemm::THREADS),                   \
+                      gemm::Cfg<E, BNV>::SMEM_BYTES, st, ta, tb, tc, p));                                           \
     }
     switch (epi) {
         case gemm::EPI_STORE_BF16: LAUNCH_GEMM(gemm::EPI_STORE_BF16, 256) break;
@@ -299,7 +318,7 @@ static int launch_layernorm(esmdiff_ctx* c, const float* x, const float* w, cons
     if (D % 128 != 0 || D > 128 * 12) return c->fail("layernorm: D must be a multiple of 128, <= 1536");
     const int grid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
     ProfScope prof(c, ESMDIFF_PROF_LAYERNORM, 6.0 * M * D, st);
-    ew::layernorm_f32_to_bf16_kernel<12><<<grid, ew::ROWS_PER_BLOCK * 32, 0, st>>>(x, w, b, y, M, D, 1e-5f);
+    CK(launch_pdl(c->pdl, ew::layernorm_f32_to_bf16_kernel<12>, dim3(grid), dim3(ew::ROWS_PER_BLOCK * 32), 0, st, x, w, b, y, M, D, 1e-5f));
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -333,8 +352,8 @@ static int launch_qk_norm_rope(esmdiff_ctx* c, bf16* qkv, const float* qw, const
     if (ensure_rope(c, T, st)) return 1;
     const int grid = (M + ew::ROWS_PER_BLOCK - 1) / ew::ROWS_PER_BLOCK;
     ProfScope prof(c, ESMDIFF_PROF_QK_NORM_ROPE, 8.0 * M * D, st);
-    ew::qk_layernorm_rope_kernel<6><<<grid, ew::ROWS_PER_BLOCK * 32, 0, st>>>(qkv, qw, kw, c->cos_t,
-                                                                               c->sin_t, M, D, T, 1e-5f);
+    CK(launch_pdl(c->pdl, ew::qk_layernorm_rope_kernel<6>, dim3(grid), dim3(ew::ROWS_PER_BLOCK * 32), 0, st, qkv, qw, kw,
+                  c->cos_t, c->sin_t, M, D, T, 1e-5f));
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -362,7 +381,7 @@ static int launch_attention_streaming(esmdiff_ctx* c, const bf16* qkv, bf16* out
     }
     const int grid = B * H * p.q_tiles;
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn::DH, st);
-    attn::attention_fwd_kernel<<<grid, attn::THREADS, smem, st>>>(tq, tkv, p);
+    CK(launch_pdl(c->pdl, attn::attention_fwd_kernel, dim3(grid), dim3(attn::THREADS), smem, st, tq, tkv, p));
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -402,7 +421,7 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
         c->attn_resident_smem = smem;
     }
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn2::DH, st);
-    attn2::attention_resident_kernel<<<B * H, attn2::THREADS, smem, st>>>(tq, tkv, tkvt, p);
+    CK(launch_pdl(c->pdl, attn2::attention_resident_kernel, dim3(B * H), dim3(attn2::THREADS), smem, st, tq, tkv, tkvt, p));
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -411,9 +430,10 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
 static int launch_time_embed(esmdiff_ctx* c, float sigma, float* cond, cudaStream_t st) {
     const int D = c->cfg.d_model;
     if (!c->cfg.time_conditioning) sigma = 0.f;           // model.py:538-539
-    ew::time_embed_hidden_kernel<<<(D + 7) / 8, 256, 0, st>>>(sigma, c->te_w0, c->te_b0, c->te_hidden, D,
-                                                              c->cfg.time_freq_dim);
-    ew::time_embed_out_kernel<<<(D + 7) / 8, 256, 0, st>>>(c->te_hidden, c->te_w2, c->te_b2, cond, D);
+    CK(launch_pdl(c->pdl, ew::time_embed_hidden_kernel, dim3((D + 7) / 8), dim3(256), 0, st, sigma, c->te_w0, c->te_b0,
+                  c->te_hidden, D, c->cfg.time_freq_dim));
+    CK(launch_pdl(c->pdl, ew::time_embed_out_kernel, dim3((D + 7) / 8), dim3(256), 0, st, c->te_hidden, c->te_w2, c->te_b2,
+                  cond, D));
     c->launches += 2;
     CK(cudaGetLastError());
     return 0;
@@ -817,6 +837,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
         c->attn_variant = strcmp(e, "stream") == 0 ? 1 : strcmp(e, "tiles") == 0 ? 2 : 0;
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
+    if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;
@@ -963,7 +984,7 @@ int esmdiff_finalize_weights(esmdiff_ctx* c) {
             }
             ew::fold_layernorm_weight_kernel<<<(unsigned)((3 * D + 7) / 8), 256>>>(w.wqkv_f32, w.ln1_w, w.ln1_b, w.wqkv,
                                                                                    w.cqkv, w.bqkv, 3 * D, D, 0, colmean,
-                                                                                   2 * D, D);
+                                                                                   c->qk_fused ? 2 * D : 0, D);
             ew::fold_layernorm_weight_kernel<<<(unsigned)((2 * F + 7) / 8), 256>>>(w.w1_f32, w.ln2_w, w.ln2_b, w.w1, w.c1,
                                                                                    w.b1, 2 * F, D, (int)F);
             CK(cudaGetLastError());

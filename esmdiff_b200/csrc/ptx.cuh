@@ -24,6 +24,15 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
+// ---- programmatic dependent launch ---------------------------------------------------------
+// Kernels of the forward are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a
+// kernel may become resident (barrier init, TMEM allocation, descriptor prefetch) while its
+// predecessor in the stream drains, and blocks in pdl_wait() until that predecessor has COMPLETED
+// and its writes are visible.  Rule kept by every kernel here: no global-memory read or write before
+// pdl_wait().  Both are no-ops when the launch carries no such attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(THREADS)
 sample_rows_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ u,
                    long long* __restrict__ x, float* __restrict__ out_logp, int M, int V,
                    int mask_index, float mc_t, float mc_s, unsigned long long seed, uint32_t step) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[THREADS / 32];
     __shared__ int red_i[THREADS / 32];
     const int row = blockIdx.x;

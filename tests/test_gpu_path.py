@@ -54,12 +54,13 @@ def parity(logits, xt, ref_logits, emul_logits, emb=None, ref_emb=None):
     logits, xt = logits.float().cpu(), xt.cpu()
     lp = masked_logp(logits, xt)
     lp_ref, lp_emu = masked_logp(ref_logits, xt), masked_logp(emul_logits, xt)
+    mx = lambda t: float(t.abs().max()) if t.numel() else 0.0            # late steps: no masked row left
     out = {"lp_rel_fp32": rel_fro(lp, lp_ref), "lp_rel_emul": rel_fro(lp, lp_emu),
-           "lp_maxabs_fp32": float((lp - lp_ref).abs().max()), "lp_maxabs_emul": float((lp - lp_emu).abs().max()),
+           "lp_maxabs_fp32": mx(lp - lp_ref), "lp_maxabs_emul": mx(lp - lp_emu),
            "raw_rel_fp32": rel_fro(logits, ref_logits), "raw_rel_emul": rel_fro(logits, emul_logits),
            "emul_vs_fp32_raw": rel_fro(emul_logits, ref_logits),
-           "top1_fp32": float((lp.argmax(-1) == lp_ref.argmax(-1)).float().mean()),
-           "top1_emul": float((lp.argmax(-1) == lp_emu.argmax(-1)).float().mean())}
+           "top1_fp32": float((lp.argmax(-1) == lp_ref.argmax(-1)).float().mean()) if lp.numel() else 1.0,
+           "top1_emul": float((lp.argmax(-1) == lp_emu.argmax(-1)).float().mean()) if lp.numel() else 1.0}
     if emb is not None:
         out["emb_rel_fp32"] = rel_fro(emb.float().cpu(), ref_emb)
         assert out["emb_rel_fp32"] < EMB_REL_FP32_MAX, out
