@@ -60,21 +60,19 @@ struct Params {
     float ln_eps;               // q_ln / k_ln epsilon
 };
 
-// 1 / sqrt(mean (y - mean y)^2 + eps) of one q or k row from its partial sums of squares.
-__device__ __forceinline__ float row_rstd(const float* part, int nspan, float ln_eps) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 12; ++i)
-        if (i < nspan) s += __ldg(part + i);
-    return rsqrtf(s / static_cast<float>(nspan * 128) + ln_eps);
-}
-
 __host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
     return (nkv - 1) * KV_TILE_BYTES + tail_cols * 128;
 }
 __host__ __device__ inline int left_bytes(int nkv) { return MAX_LEFT * nkv * BKV * 4; }   // fp32 p per leftover row
+__host__ __device__ inline int rstd_bytes(int nkv) { return 2 * nkv * BKV * 4; }          // 1/std of every k row, then q row
 __host__ inline int smem_bytes(int nkv, int tail_cols) {
-    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + BAR_BYTES + left_bytes(nkv);
+    return 1024 + 2 * Q_BYTES + 2 * kv_bytes(nkv, tail_cols) + BAR_BYTES + left_bytes(nkv) + rstd_bytes(nkv);
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // One trailing query row on CUDA cores (one warp), K and V read from the swizzled shared-memory
@@ -189,6 +187,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint64_t* k_scaled = v_full + MAX_KV_TILES;           // [MAX_KV_TILES], single use: K tile multiplied by rstd_k
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_scaled + MAX_KV_TILES);
     float* left_p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [MAX_LEFT][nkv * 64]
+    float* rstd_k = left_p + MAX_LEFT * p.nkv * BKV;                                          // [nkv * 64]
+    float* rstd_q = rstd_k + p.nkv * BKV;                                                     // [nkv * 64] (>= T)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -231,6 +231,51 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
     if (warp != 5) pdl_wait();             // every role but the MMA issuer touches global memory
+
+    if (fused_ln) {
+        // 1/std of every k row and q row of this (sample, head)'s sample from the QKV epilogue's partial
+        // sums of squares, into shared memory, by the six warps that have nothing to do until the first
+        // tiles land.  The TMA warp holds its loads back until the first batch of these small loads is in
+        // flight (named barrier 1): issued behind 82 KB of tile traffic per CTA they came back ~5k clk
+        // late, and the first S MMA needs the k factors (ncu r2c: +8k clk per CTA).
+        if (warp != 4 && warp != 5) {
+            const int tid = warp < 4 ? threadIdx.x : threadIdx.x - 64;       // 0..191
+            const int n = 2 * p.T;                                             // k rows, then q rows
+            const int half = p.nspan >> 1;
+            const float inv_n = 1.0f / static_cast<float>(p.nspan * 128);
+            bool released = false;
+#pragma unroll 1
+            for (int base = 0; base < n; base += 4 * 192) {
+                float2 raw[4][6];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int idx = base + b * 192 + tid;
+                    const bool isq = idx >= p.T;
+                    const int row = isq ? idx - p.T : idx;
+                    const float2* src = reinterpret_cast<const float2*>(
+                        p.qk_sumsq + static_cast<long long>(row0 + row) * 2 * p.nspan + (isq ? 0 : p.nspan));
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+                        raw[b][i] = (idx < n && i < half) ? __ldg(src + i) : make_float2(0.f, 0.f);
+                }
+                if (!released) {
+                    named_bar_arrive(1, 224);
+                    released = true;
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int idx = base + b * 192 + tid;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) sum += raw[b][i].x + raw[b][i].y;
+                    if (idx < n) (idx >= p.T ? rstd_q[idx - p.T] : rstd_k[idx]) = rsqrtf(sum * inv_n + p.ln_eps);
+                }
+            }
+            named_bar_sync(2, 192);
+        } else if (warp == 4) {
+            named_bar_sync(1, 224);
+        }
+    }
 
     if (warp == 4) {
         // ===================== TMA producer =====================
@@ -330,23 +375,10 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             // row of the 64-row tile; the eight 16-byte chunks of a row are visited in a lane-rotated
             // order so that the 8 lanes of a quarter warp (rows 128 bytes apart) hit different banks
             const int tr = threadIdx.x - 6 * 32;
-            // all statistics first (independent loads, one memory latency for the whole K), then tile by
-            // tile as the TMA loads land: the first S MMA waits for tile 0 only
-            float rks[MAX_KV_TILES];
-#pragma unroll
-            for (int j = 0; j < MAX_KV_TILES; ++j) {
-                const int t = j * BKV + tr;
-                rks[j] = (j < nkv && t < p.T)
-                             ? row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan + p.nspan, p.nspan, p.ln_eps)
-                             : 0.f;
-            }
 #pragma unroll 1
             for (int j = 0; j < nkv; ++j) {
                 const bool live = j * BKV + tr < p.T;
-                float rk = rks[0];                     // select, not index: rks stays in registers
-#pragma unroll
-                for (int k = 1; k < MAX_KV_TILES; ++k)
-                    if (j == k) rk = rks[k];
+                const float rk = live ? rstd_k[j * BKV + tr] : 0.f;
                 mbar_wait(&k_full[j], 0);
                 if (live) {
                     uint8_t* rowp = sK + j * KV_TILE_BYTES + tr * 128;
@@ -370,7 +402,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         if (lw < p.n_left) {
             const int t = p.nq * BQ + lw;
             float sc = p.scale_log2;
-            if (fused_ln) sc *= row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan, p.nspan, p.ln_eps);
+            if (fused_ln) sc *= rstd_q[t];
             leftover_row(p.qkv + static_cast<long long>(row0 + t) * 3 * D + h * DH,
                          p.ctx + static_cast<long long>(row0 + t) * D + h * DH, sK, sV, left_p + lw * nkv * BKV, p.T,
                          sc, k_ready, v_full, nkv, lane);
@@ -382,16 +414,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         const uint32_t t_o = tmem_base + lane_addr + COL_O;
         float sc = p.scale_log2;              // per query row once q_ln's 1/std is folded in (set per query tile)
         float thresh = RESCALE_LOG2 / sc;
-        constexpr int MAX_Q_TILES = (MAX_KV_TILES * BKV + BQ - 1) / BQ;
-        float rqs[MAX_Q_TILES];               // 1/std of this thread's query row in every query tile, fetched up front
-#pragma unroll
-        for (int qt = 0; qt < MAX_Q_TILES; ++qt) {
-            const int t = qt * BQ + r;
-            rqs[qt] = (fused_ln && qt < nq && t < p.T)
-                          ? row_rstd(p.qk_sumsq + static_cast<long long>(row0 + t) * 2 * p.nspan, p.nspan, p.ln_eps)
-                          : 1.0f;
-        }
-
         // out[row] = O / l for query tile qt (after its last PV has retired), then free O
         auto epilogue = [&](int qt, float l) {
             mbar_wait(o_full, qt & 1);
@@ -433,11 +455,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                     l_prev = l_run;
                     l_run = 0.f;
                     if (fused_ln) {
-                        float rq = rqs[0];                 // select, not index: rqs stays in registers
-#pragma unroll
-                        for (int k = 1; k < MAX_Q_TILES; ++k)
-                            if (qt == k) rq = rqs[k];
-                        sc = p.scale_log2 * rq;
+                        const int t = qt * BQ + r;
+                        sc = p.scale_log2 * (t < p.T ? rstd_q[t] : 1.0f);
                         thresh = RESCALE_LOG2 / sc;
                     }
                 }

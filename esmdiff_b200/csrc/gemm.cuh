@@ -89,7 +89,12 @@ template <int EPI, int BN> struct Cfg {
     static constexpr int B_BYTES = BN_CTA * BK * 2;       // 16 / 12 KiB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BOXES = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN) ? 0 : 1;    // the residual epilogue stages nothing
-    static constexpr int STG_BYTES = EPI_WARPS * BOXES * BOX_BYTES;
+    // EPI_QKV_ROPE_LN: per epilogue warp, the three per-column vectors (colsum, bias, q/k gamma) of its
+    // 128 columns, fetched once per tile while the main loop runs and then read as shared-memory
+    // broadcasts (ncu r2c: as direct global loads right before their use they cost the epilogue an
+    // exposed L2 round trip per 16 columns -- 7.2k of 13.8k stall samples -- and the tensor pipe 15 points)
+    static constexpr int VEC_BYTES = EPI == EPI_QKV_ROPE_LN ? 3 * 128 * 4 : 0;
+    static constexpr int STG_BYTES = EPI_WARPS * (BOXES * BOX_BYTES + VEC_BYTES);
     static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STG_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_FIT < MAX_STAGES ? STAGES_FIT : MAX_STAGES;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + 512;
@@ -202,6 +207,15 @@ __device__ __forceinline__ void ld_uniform(float* r, const float* g) {
 #pragma unroll
     for (int i = 0; i < N / 4; ++i) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+    }
+}
+// The same from shared memory (one broadcast read per 16 bytes).
+template <int N>
+__device__ __forceinline__ void ld_uniform_smem(float* r, const float* s) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(s)[i];
         r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
     }
 }
@@ -392,7 +406,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         // ===================== epilogue warps (both CTAs) =====================
         const int q = warp & 3;                       // TMEM lanes [32 q, 32 q + 32)
         const int half = warp >> 2;                   // accumulator columns [128 half, 128 half + 128)
-        uint8_t* box = stg_all + warp * BOXES * BOX_BYTES;
+        uint8_t* box = stg_all + warp * (BOXES * BOX_BYTES + C::VEC_BYTES);
+        float* vec = reinterpret_cast<float*>(box + BOXES * BOX_BYTES);      // [3][128]: colsum | bias | gamma (EPI_QKV_ROPE_LN)
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr bool RESID = EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN;
@@ -401,6 +416,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         constexpr bool ROPE = EPI == EPI_QKV_ROPE_LN;
         float rcos[ROPE ? 32 : 1], rsin[ROPE ? 32 : 1];   // rotary table row of this thread's token position
         int rope_mt = -1;                             // row tile the table row was loaded for
+        int stat_mt = -1;                             // row tile rstd_c / nrm_c belong to
+        float rstd_c = 0.f, nrm_c = 0.f;
         for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
             const int nb = tile % p.n_tiles;
             const int n0 = nb * BN + half * (BN / 2);
@@ -471,12 +488,32 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 // out = rstd * acc + (b[n] - rstd * mean * c[n]); the row statistics are fetched
                 // while the main loop of this tile is still running
                 float rstd, nrm;
-                row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
-                              row_base + lane < p.M, p.ln_eps, rstd, nrm);
                 bool rot = false;
                 if constexpr (ROPE) {
+                    // contiguous tile ranges: consecutive tiles share their rows, so the row statistics
+                    // and the rotary table row are fetched once per row tile
                     rot = n0 < p.n_rope;                           // warp-uniform: a q or k column tile
                     const int mt = tile / p.n_tiles;
+                    if (mt != stat_mt) {
+                        row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
+                                      row_base + lane < p.M, p.ln_eps, rstd_c, nrm_c);
+                        stat_mt = mt;
+                    }
+                    rstd = rstd_c;
+                    nrm = nrm_c;
+                    // this warp's 128 columns of colsum / bias / gamma -> shared memory (latency hidden
+                    // behind the wait for the accumulators)
+                    __syncwarp();
+                    {
+                        const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colsum + n0) + lane);
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + lane);
+                        float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                        if (rot) g4 = __ldg(reinterpret_cast<const float4*>(p.qk_gamma + n0) + lane);
+                        reinterpret_cast<float4*>(vec)[lane] = c4;
+                        reinterpret_cast<float4*>(vec + 128)[lane] = b4;
+                        reinterpret_cast<float4*>(vec + 256)[lane] = g4;
+                    }
+                    __syncwarp();
                     if (rot && mt != rope_mt) {
                         const int row = row_base + lane < p.M ? row_base + lane : p.M - 1;
                         const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(row % p.T) * 64);
@@ -488,6 +525,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         }
                         rope_mt = mt;
                     }
+                } else {
+                    row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
+                                  row_base + lane < p.M, p.ln_eps, rstd, nrm);
                 }
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
@@ -496,22 +536,44 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     for (int c = 0; c < (BN / 2) / 64; ++c) {
                         if (lane == 0) bulk_wait_group_read<0>();     // the previous store has read the box
                         __syncwarp();
+                        if constexpr (ROPE) {
+                            // v column tiles of the QKV projection: 16 columns at a time (this kernel keeps
+                            // 64 registers of rotary table per thread)
 #pragma unroll 1
-                        for (int hh = 0; hh < 2; ++hh) {
-                            uint32_t v[32];
-                            float cs[32], bs[32];
-                            tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
-                            ld_uniform<32>(cs, p.colsum + n0 + c * 64 + hh * 32);
-                            ld_uniform<32>(bs, p.bias + n0 + c * 64 + hh * 32);
-                            tmem_ld_wait();
-                            float y[32];
+                            for (int hh = 0; hh < 4; ++hh) {
+                                uint32_t v[16];
+                                float cs[16], bs[16];
+                                tmem_ld_32x32b_x16(t_row + c * 64 + hh * 16, v);
+                                ld_uniform_smem<16>(cs, vec + c * 64 + hh * 16);
+                                ld_uniform_smem<16>(bs, vec + 128 + c * 64 + hh * 16);
+                                tmem_ld_wait();
+                                float y[16];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), rstd, fmaf(nrm, cs[j], bs[j]));
+                                for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(v[j]), rstd, fmaf(nrm, cs[j], bs[j]));
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                st_swz16(box, lane, hh * 4 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
-                                         pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
-                                         pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                                for (int j = 0; j < 2; ++j)
+                                    st_swz16(box, lane, hh * 2 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
+                                             pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
+                                             pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int hh = 0; hh < 2; ++hh) {
+                                uint32_t v[32];
+                                float cs[32], bs[32];
+                                tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
+                                ld_uniform<32>(cs, p.colsum + n0 + c * 64 + hh * 32);
+                                ld_uniform<32>(bs, p.bias + n0 + c * 64 + hh * 32);
+                                tmem_ld_wait();
+                                float y[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) y[j] = fmaf(__uint_as_float(v[j]), rstd, fmaf(nrm, cs[j], bs[j]));
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    st_swz16(box, lane, hh * 4 + j, pack_bf16x2(y[8 * j], y[8 * j + 1]),
+                                             pack_bf16x2(y[8 * j + 2], y[8 * j + 3]), pack_bf16x2(y[8 * j + 4], y[8 * j + 5]),
+                                             pack_bf16x2(y[8 * j + 6], y[8 * j + 7]));
+                            }
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
@@ -531,33 +593,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         if (lane == 0) bulk_wait_group_read<0>();
                         __syncwarp();
 #pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            uint32_t v[32];
-                            const int na = n0 + c * 64 + hh * 32;
-                            tmem_ld_32x32b_x32(t_row + c * 64 + hh * 32, v);
+                        for (int hq = 0; hq < 4; ++hq) {                   // 16 columns = 8 rotary pairs at a time
+                            uint32_t v[16];
+                            float cs[16], bs[16], gs[16];
+                            const int vo = c * 64 + hq * 16;
+                            tmem_ld_32x32b_x16(t_row + vo, v);
+                            ld_uniform_smem<16>(cs, vec + vo);
+                            ld_uniform_smem<16>(bs, vec + 128 + vo);
+                            ld_uniform_smem<16>(gs, vec + 256 + vo);
                             tmem_ld_wait();
-                            uint32_t o[16];
+                            uint32_t o[8];
 #pragma unroll
-                            for (int h2 = 0; h2 < 2; ++h2) {               // 16 columns = 8 rotary pairs at a time
-                                float cs[16], bs[16], gs[16];
-                                ld_uniform<16>(cs, p.colsum + na + h2 * 16);
-                                ld_uniform<16>(bs, p.bias + na + h2 * 16);
-                                ld_uniform<16>(gs, p.qk_gamma + na + h2 * 16);
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const int i = h2 * 16 + 2 * e;
-                                    const float ya = fmaf(__uint_as_float(v[i]), rstd, fmaf(nrm, cs[2 * e], bs[2 * e]));
-                                    const float yb = fmaf(__uint_as_float(v[i + 1]), rstd, fmaf(nrm, cs[2 * e + 1], bs[2 * e + 1]));
-                                    sq = fmaf(ya, ya, sq);
-                                    sq = fmaf(yb, yb, sq);
-                                    const float za = ya * gs[2 * e], zb = yb * gs[2 * e + 1];
-                                    const float cc = rcos[hh * 16 + h2 * 8 + e], ss = rsin[hh * 16 + h2 * 8 + e];
-                                    o[h2 * 8 + e] = pack_bf16x2(fmaf(za, cc, -(zb * ss)),      // x1 cos - x2 sin
-                                                                fmaf(zb, cc, za * ss));        // x2 cos + x1 sin
-                                }
+                            for (int e = 0; e < 8; ++e) {
+                                const float ya = fmaf(__uint_as_float(v[2 * e]), rstd, fmaf(nrm, cs[2 * e], bs[2 * e]));
+                                const float yb = fmaf(__uint_as_float(v[2 * e + 1]), rstd, fmaf(nrm, cs[2 * e + 1], bs[2 * e + 1]));
+                                sq = fmaf(ya, ya, sq);
+                                sq = fmaf(yb, yb, sq);
+                                const float za = ya * gs[2 * e], zb = yb * gs[2 * e + 1];
+                                const float cc = rcos[hq * 8 + e], ss = rsin[hq * 8 + e];
+                                o[e] = pack_bf16x2(fmaf(za, cc, -(zb * ss)),      // x1 cos - x2 sin
+                                                   fmaf(zb, cc, za * ss));        // x2 cos + x1 sin
                             }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) st_swz16(box, lane, hh * 4 + j, o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                            st_swz16(box, lane, hq * 2, o[0], o[1], o[2], o[3]);
+                            st_swz16(box, lane, hq * 2 + 1, o[4], o[5], o[6], o[7]);
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
