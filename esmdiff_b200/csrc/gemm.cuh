@@ -406,8 +406,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         // ===================== epilogue warps (both CTAs) =====================
         const int q = warp & 3;                       // TMEM lanes [32 q, 32 q + 32)
         const int half = warp >> 2;                   // accumulator columns [128 half, 128 half + 128)
-        uint8_t* box = stg_all + warp * (BOXES * BOX_BYTES + C::VEC_BYTES);
-        float* vec = reinterpret_cast<float*>(box + BOXES * BOX_BYTES);      // [3][128]: colsum | bias | gamma (EPI_QKV_ROPE_LN)
+        uint8_t* box = stg_all + warp * BOXES * BOX_BYTES;      // 1024-byte aligned: the 128B swizzle is a function of the address
+        float* vec = reinterpret_cast<float*>(stg_all + EPI_WARPS * BOXES * BOX_BYTES + warp * C::VEC_BYTES);   // [3][128]: colsum | bias | gamma
         int acc = 0;
         uint32_t acc_phase = 0;
         constexpr bool RESID = EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN;
