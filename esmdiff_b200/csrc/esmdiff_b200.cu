@@ -79,6 +79,7 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    int qkv_run = -1;          // tile schedule of the QKV GEMM with the RoPE epilogue (gemm.cuh TileSchedule); ESMDIFF_QKV_RUN
     bool pdl = true;           // programmatic dependent launch between the kernels of a forward; ESMDIFF_PDL=0 -> off
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
@@ -276,6 +277,7 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     p.stats_in = ln.stats_in; p.colsum = ln.colsum; p.stats_out = ln.stats_out; p.xb_out = ln.xb_out;
     p.ln_eps = 1e-5f;
     p.rope = ln.rope; p.qk_gamma = ln.qk_gamma; p.qk_sumsq = ln.qk_sumsq; p.T = ln.T; p.n_rope = ln.n_rope;
+    p.run = c->qkv_run > 0 && p.n_tiles % c->qkv_run != 0 ? -1 : c->qkv_run;
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = 2 * (tiles < max_clusters ? tiles : max_clusters);
     // profile kinds: the LayerNorm-folded variants are booked under their plain counterparts
@@ -838,6 +840,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
+    if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;

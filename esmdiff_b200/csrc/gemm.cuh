@@ -120,6 +120,7 @@ struct Params {
     float* qk_sumsq;           // [M][n_rope / 128]: sum over each 128-column span of (q - mean q)^2, (k - mean k)^2
     int T;                     // tokens per sample
     int n_rope;                // columns [0, n_rope) are q | k (multiple of 256); the rest (v) is stored as is
+    int run;                   // EPI_QKV_ROPE_LN tile schedule (TileSchedule): 0 strided, R > 0 runs of R column tiles, < 0 contiguous ranges
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -260,25 +261,46 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                  : "memory");
 }
 
-// Tile schedule of one CTA pair.  Strided (tile = cluster, cluster + n_clusters, ...) for every
-// epilogue except EPI_QKV_ROPE_LN, which walks a CONTIGUOUS range of the (row tile, column tile)
-// list, column tile fastest: consecutive tiles then share their token rows, and the rotary table
-// row each epilogue thread needs (64 fp32, one row per thread = 32 L1 wavefronts per load
-// instruction) stays in registers across the ~12 q/k column tiles of a row tile instead of being
-// re-read per tile.
-template <int EPI>
-struct TileRange {
-    int begin, end, step;
-    __device__ TileRange(int cluster_id, int num_clusters, int num_tiles) {
-        if constexpr (EPI == EPI_QKV_ROPE_LN) {
-            begin = static_cast<int>(static_cast<long long>(cluster_id) * num_tiles / num_clusters);
-            end = static_cast<int>(static_cast<long long>(cluster_id + 1) * num_tiles / num_clusters);
-            step = 1;
+// Tile schedule of one CTA pair over the (row tile, column tile) list, column tile fastest.
+//   run == 0 : strided -- tile = cluster, cluster + n_clusters, ...  (every epilogue but EPI_QKV_ROPE_LN)
+//   run == R : units of R consecutive column tiles of one row tile, units strided over the clusters.
+//              Consecutive tiles of a unit share their token rows, so the rotary table row each
+//              EPI_QKV_ROPE_LN epilogue thread needs (64 fp32, one row per thread = 32 L1 wavefronts per
+//              load instruction) and the row statistics stay in registers for R tiles.  R must divide
+//              n_tiles; the cost is coarser load balance (units of R tiles per cluster).
+//   run < 0  : one CONTIGUOUS range of the list per cluster: maximal reuse and perfect balance, but all
+//              74 clusters then sit on different A row tiles for the whole kernel (58 MB live in L2
+//              beside 240 MB of streamed output; needs the evict-last hint on A, see the TMA producer).
+struct TileSchedule {
+    int count;                              // tiles of this cluster
+    int mode, a, b, c, n_tiles;
+    __device__ TileSchedule(int run, int cluster_id, int num_clusters, int num_tiles, int n_tiles_) {
+        n_tiles = n_tiles_;
+        if (run < 0) {
+            mode = 2;
+            a = static_cast<int>(static_cast<long long>(cluster_id) * num_tiles / num_clusters);
+            count = static_cast<int>(static_cast<long long>(cluster_id + 1) * num_tiles / num_clusters) - a;
+            b = c = 0;
+        } else if (run == 0) {
+            mode = 0;
+            a = cluster_id;
+            b = num_clusters;
+            c = 0;
+            count = cluster_id < num_tiles ? (num_tiles - cluster_id + num_clusters - 1) / num_clusters : 0;
         } else {
-            begin = cluster_id;
-            end = num_tiles;
-            step = num_clusters;
+            mode = 1;
+            a = cluster_id;
+            b = num_clusters;
+            c = run;
+            const int units = num_tiles / run;
+            count = cluster_id < units ? (units - cluster_id + num_clusters - 1) / num_clusters * run : 0;
         }
+    }
+    __device__ __forceinline__ int tile_at(int i) const {
+        if (mode == 2) return a + i;
+        if (mode == 0) return a + i * b;
+        const int u = a + (i / c) * b, per_row = n_tiles / c;
+        return (u / per_row) * n_tiles + (u % per_row) * c + i % c;
     }
 };
 
@@ -311,7 +333,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
     const int num_clusters = gridDim.x >> 1;
     const int num_tiles = p.m_tiles * p.n_tiles;
     const int kblocks = p.K / BK;
-    const TileRange<EPI> tr(cluster_id, num_clusters, num_tiles);
+    const TileSchedule sched(EPI == EPI_QKV_ROPE_LN ? p.run : 0, cluster_id, num_clusters, num_tiles, p.n_tiles);
 
     if (warp == WARP_TMA && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -345,7 +367,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             pdl_wait();                    // A (and any other input) is complete and visible
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
+            for (int it = 0; it < sched.count; ++it) {
+                const int tile = sched.tile_at(it);
                 const int m0 = (tile / p.n_tiles) * BM + rank * BM_CTA;
                 const int n0 = (tile % p.n_tiles) * BN + rank * BN_CTA;
                 for (int kb = 0; kb < kblocks; ++kb) {
@@ -353,7 +376,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[stage]), 0);
                     if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
-                    tma_load_2d_pair(sa, &tmA, leader_full, kb * BK, m0);
+                    if constexpr (EPI == EPI_QKV_ROPE_LN) {
+                        // contiguous tile ranges: a CTA pair re-reads ITS A row tile for ~18 consecutive column
+                        // tiles while the chip streams 240 MB of q|k|v through L2 -- without a hint the A tiles
+                        // are evicted in between and come back from DRAM (ncu r2e: 793 MB of DRAM reads against
+                        // 96 MB for the strided schedule, tensor pipe 79 %): keep A, let the output go first
+                        tma_load_2d_pair_hint(sa, &tmA, leader_full, kb * BK, m0, L2_EVICT_LAST);
+                    } else {
+                        tma_load_2d_pair(sa, &tmA, leader_full, kb * BK, m0);
+                    }
                     tma_load_2d_pair(sa + A_BYTES, &tmB, leader_full, kb * BK, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -372,7 +403,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
+            for (int it = 0; it < sched.count; ++it) {
+                const int tile = sched.tile_at(it);
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
@@ -418,7 +450,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
         int rope_mt = -1;                             // row tile the table row was loaded for
         int stat_mt = -1;                             // row tile rstd_c / nrm_c belong to
         float rstd_c = 0.f, nrm_c = 0.f;
-        for (int tile = tr.begin; tile < tr.end; tile += tr.step) {
+        for (int it = 0; it < sched.count; ++it) {
+            const int tile = sched.tile_at(it);
             const int nb = tile % p.n_tiles;
             const int n0 = nb * BN + half * (BN / 2);
             const int row_base = (tile / p.n_tiles) * BM + rank * BM_CTA + q * 32;
@@ -578,7 +611,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmC, box, n0 + c * 64, row_base);
+                            if constexpr (ROPE) tma_store_2d_hint(&tmC, box, n0 + c * 64, row_base, L2_EVICT_FIRST);
+                            else tma_store_2d(&tmC, box, n0 + c * 64, row_base);
                             bulk_commit_group();
                         }
                     }
@@ -620,7 +654,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmC, box, n0 + c * 64, row_base);
+                            if constexpr (ROPE) tma_store_2d_hint(&tmC, box, n0 + c * 64, row_base, L2_EVICT_FIRST);
+                            else tma_store_2d(&tmC, box, n0 + c * 64, row_base);
                             bulk_commit_group();
                         }
                     }
@@ -703,11 +738,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         if (k < nr) ld_quad(xr + 4 * k, src + static_cast<long long>(k) * p.ldo);
                 };
                 const int nr = rows_left(tile);
-                if (tile == cluster_id) {               // first tile of this CTA pair: nothing prefetched yet
+                if (it == 0) {                          // first tile of this CTA pair: nothing prefetched yet
                     ld_chunk(xres, tile, 0);
                     ld_chunk(xres + 32, tile, 1);
                 }
-                const int nt = tile + num_clusters;
+                const int nt = it + 1 < sched.count ? sched.tile_at(it + 1) : num_tiles;
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
                 // EPI_RESID_F32_LN: (sum, sum of squares) of my 4 columns of each of the 8 rows, over

@@ -160,6 +160,24 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         "r"(c_inner), "r"(c_outer)
         : "memory");
 }
+// The same with an L2 eviction-priority hint (createpolicy encodings as CUTLASS's TMA::CacheHintSm90).
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
+                                                      int c_inner, int c_outer, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr),
+        "r"(c_inner), "r"(c_outer), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* tm, const void* smem_src, int c_inner, int c_outer,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
                  "r"(ncols)

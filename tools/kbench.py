@@ -150,6 +150,13 @@ def bench_qk(flush):
         t_rope = timeit(lambda: e.op_gemm_qkv_rope(xb, wfc, bsc, stats, csc, gam, T, 2 * D), flush=flush)
         t_row = timeit(lambda: e.op_qk_norm_rope(qkv, ones, ones, B, T), flush=flush)
         qkv2, sumsq = e.op_gemm_qkv_rope(xb, wfc, bsc, stats, csc, gam, T, 2 * D)
+        runs = ""
+        for run in ("0", "2", "3", "6", "9"):
+            er = engine(ESMDIFF_QKV_RUN=run)
+            tr_ = timeit(lambda: er.op_gemm_qkv_rope(xb, wfc, bsc, stats, csc, gam, T, 2 * D), flush=flush)
+            runs += f" run={run}: {tr_ * 1e3:.1f} us"
+            er.close()
+        print(f"  B={B} T={T}: QKV + rope epilogue by tile schedule (default = contiguous ranges {t_rope * 1e3:.1f} us):{runs}", flush=True)
         t_att = timeit(lambda: e.op_attention(qkv, B, T, H), flush=flush)
         t_att_ln = timeit(lambda: e.op_attention(qkv2, B, T, H, qk_sumsq=sumsq), flush=flush)
         fl = 2.0 * M * 3 * D * D
