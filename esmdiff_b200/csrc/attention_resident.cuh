@@ -370,35 +370,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     } else if (warp >= 6) {
         // ===================== trailing query rows past the last full tile =====================
         const int lw = warp - 6;
-        if (fused_ln) {
-            // K rows *= rstd_k (q_ln / k_ln folded into the QKV epilogue, see the header): thread =
-            // row of the 64-row tile; the eight 16-byte chunks of a row are visited in a lane-rotated
-            // order so that the 8 lanes of a quarter warp (rows 128 bytes apart) hit different banks
-            const int tr = threadIdx.x - 6 * 32;
-#pragma unroll 1
-            for (int j = 0; j < nkv; ++j) {
-                const bool live = j * BKV + tr < p.T;
-                const float rk = live ? rstd_k[j * BKV + tr] : 0.f;
-                mbar_wait(&k_full[j], 0);
-                if (live) {
-                    uint8_t* rowp = sK + j * KV_TILE_BYTES + tr * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4* cp = reinterpret_cast<uint4*>(rowp + (((c + lane) & 7) << 4));
-                        const uint4 v = *cp;
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                        uint32_t o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            o[e] = pack_bf16x2(__uint_as_float(w[e] << 16) * rk, __uint_as_float(w[e] & 0xffff0000u) * rk);
-                        *cp = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-                fence_proxy_async_smem();          // generic-proxy writes -> visible to the UMMA reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&k_scaled[j]);
-            }
-        }
         if (lw < p.n_left) {
             const int t = p.nq * BQ + lw;
             float sc = p.scale_log2;
@@ -443,6 +414,38 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             if (lane == 0) mbar_arrive(o_free);
         };
 
+        if (fused_ln) {
+            // K rows *= rstd_k (q_ln / k_ln folded into the QKV epilogue, see the header), by the softmax
+            // warps before their first S tile lands (they are idle until then): warps 0-1 take the even
+            // kv tiles, warps 2-3 the odd ones, thread = row of the 64-row tile; the eight 16-byte chunks
+            // of a row are visited in a lane-rotated order so that the 8 lanes of a quarter warp (rows 128
+            // bytes apart) hit different banks.  (First version: warps 6-7, which delayed their trailing
+            // query rows by the whole K pass.)
+            const int tr = threadIdx.x & 63;
+#pragma unroll 1
+            for (int j = warp >> 1; j < nkv; j += 2) {
+                const bool live = j * BKV + tr < p.T;
+                const float rk = live ? rstd_k[j * BKV + tr] : 0.f;
+                mbar_wait(&k_full[j], 0);
+                if (live) {
+                    uint8_t* rowp = sK + j * KV_TILE_BYTES + tr * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        uint4* cp = reinterpret_cast<uint4*>(rowp + (((c + lane) & 7) << 4));
+                        const uint4 v = *cp;
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        uint32_t o[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            o[e] = pack_bf16x2(__uint_as_float(w[e] << 16) * rk, __uint_as_float(w[e] & 0xffff0000u) * rk);
+                        *cp = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                fence_proxy_async_smem();          // generic-proxy writes -> visible to the UMMA reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&k_scaled[j]);
+            }
+        }
         float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
         float l_run = 0.f, l_prev = 0.f;      // running row sum (relative to m_run); previous tile's final sum
 #pragma unroll 1

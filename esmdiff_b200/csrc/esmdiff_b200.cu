@@ -79,7 +79,10 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
-    int qkv_run = -1;          // tile schedule of the QKV GEMM with the RoPE epilogue (gemm.cuh TileSchedule); ESMDIFF_QKV_RUN
+    int qkv_run = 0;           // tile schedule of the QKV GEMM with the RoPE epilogue (gemm.cuh TileSchedule; measured r2f at
+                               // B=100, T=258: strided 234 us, runs of 2 / 3 / 6 column tiles 243 / 255 / 290 us, contiguous ranges
+                               // 263 us -- re-reading the rotary table row per tile is cheaper than any loss of L2 locality
+                               // or balance); ESMDIFF_QKV_RUN overrides
     bool pdl = true;           // programmatic dependent launch between the kernels of a forward; ESMDIFF_PDL=0 -> off
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
