@@ -22,10 +22,13 @@
 //   qk_sumsq != null : q' = rope(gamma_q (q - mean q)), k' likewise, NOT yet divided by their row
 //                      standard deviation, plus the per-row partial sums of (q - mean q)^2 and
 //                      (k - mean k)^2 the QKV GEMM epilogue left (gemm.cuh EPI_QKV_ROPE_LN).  The
-//                      missing factors are per-row scalars: rstd_q[i] goes into the softmax scale of
-//                      query row i (thread = row), rstd_k[j] is multiplied into row j of the
-//                      shared-memory K tile by the two otherwise idle warps before the first S MMA
-//                      reads it (one pass over K per (sample, head): 16 shared-memory accesses per row).
+//                      missing factors are per-row scalars, both applied to the fp32 scores: rstd_q[i]
+//                      goes into the softmax scale of query row i (thread = row), rstd_k[j] multiplies
+//                      score column j (one packed multiply per two scores, the factors read as
+//                      shared-memory broadcasts).  q and k are therefore rounded to bf16 exactly once.
+//                      (First version: K rows rescaled in shared memory before the first S MMA -- a
+//                      second rounding of k, a proxy fence per tile and the whole pass on the critical
+//                      path of every CTA: +15 % kernel time; this form: see DESIGN.md.)
 // Output ctx : bf16 [M, D]
 #pragma once
 #include "ptx.cuh"
@@ -83,7 +86,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int count) {
 // registers; P V: lane = two output dims, p broadcast from shared memory.  fp32 throughout.
 __device__ __forceinline__ void leftover_row(const __nv_bfloat16* __restrict__ qrow, __nv_bfloat16* __restrict__ orow,
                                              const uint8_t* sK, const uint8_t* sV, float* pf, int T, float sc,
-                                             uint64_t* k_ready, uint64_t* v_full, int nkv, int lane) {
+                                             uint64_t* k_ready, uint64_t* v_full, int nkv, int lane,
+                                             const float* rstd_k) {
     // q: every lane needs all 64 dims -> 8 x 16-byte loads of the same 128-byte row
     float q[DH];
     {
@@ -117,7 +121,8 @@ __device__ __forceinline__ void leftover_row(const __nv_bfloat16* __restrict__ q
                 a1 = fmaf(q[8 * c + 2 * e + 1], __uint_as_float(w[e] & 0xffff0000u), a1);
             }
         }
-        const float sv = k < T ? (a0 + a1) * sc : -INFINITY;
+        float sv = k < T ? (a0 + a1) * sc : -INFINITY;
+        if (rstd_k != nullptr && k < T) sv *= rstd_k[k];
         pf[k] = sv;                                    // pf holds nkv * 64 >= nk * 32 floats
         mx = fmaxf(mx, sv);
     }
@@ -184,8 +189,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint64_t* o_full = bars + 10;                         // 1    last PV of a query tile retired
     uint64_t* k_full = bars + 11;                         // [MAX_KV_TILES], single use
     uint64_t* v_full = k_full + MAX_KV_TILES;             // [MAX_KV_TILES], single use
-    uint64_t* k_scaled = v_full + MAX_KV_TILES;           // [MAX_KV_TILES], single use: K tile multiplied by rstd_k
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_scaled + MAX_KV_TILES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_full + MAX_KV_TILES);
     float* left_p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [MAX_LEFT][nkv * 64]
     float* rstd_k = left_p + MAX_LEFT * p.nkv * BKV;                                          // [nkv * 64]
     float* rstd_q = rstd_k + p.nkv * BKV;                                                     // [nkv * 64] (>= T)
@@ -199,7 +203,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     const int nq = p.nq, nkv = p.nkv;
     const int nsteps = nq * nkv;
     const bool fused_ln = p.qk_sumsq != nullptr;
-    uint64_t* k_ready = fused_ln ? k_scaled : k_full;     // what the consumers of K wait for
+    uint64_t* k_ready = k_full;                           // K tiles are consumed as the TMA loads leave them
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmQ);
@@ -217,7 +221,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         for (int j = 0; j < nkv; ++j) {
             mbar_init(&k_full[j], 1);
             mbar_init(&v_full[j], 1);
-            mbar_init(&k_scaled[j], 2);            // warps 6 and 7
         }
         fence_barrier_init();
     }
@@ -271,6 +274,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                     if (idx < n) (idx >= p.T ? rstd_q[idx - p.T] : rstd_k[idx]) = rsqrtf(sum * inv_n + p.ln_eps);
                 }
             }
+            for (int idx = p.T + tid; idx < p.nkv * BKV; idx += 192) rstd_k[idx] = 0.f;      // padding keys of the last tile
             named_bar_sync(2, 192);
         } else if (warp == 4) {
             named_bar_sync(1, 224);
@@ -376,7 +380,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             if (fused_ln) sc *= rstd_q[t];
             leftover_row(p.qkv + static_cast<long long>(row0 + t) * 3 * D + h * DH,
                          p.ctx + static_cast<long long>(row0 + t) * D + h * DH, sK, sV, left_p + lw * nkv * BKV, p.T,
-                         sc, k_ready, v_full, nkv, lane);
+                         sc, k_ready, v_full, nkv, lane, fused_ln ? rstd_k : nullptr);
         }
     } else {
         // ===================== softmax / output warps: thread = query row =====================
@@ -414,38 +418,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             if (lane == 0) mbar_arrive(o_free);
         };
 
-        if (fused_ln) {
-            // K rows *= rstd_k (q_ln / k_ln folded into the QKV epilogue, see the header), by the softmax
-            // warps before their first S tile lands (they are idle until then): warps 0-1 take the even
-            // kv tiles, warps 2-3 the odd ones, thread = row of the 64-row tile; the eight 16-byte chunks
-            // of a row are visited in a lane-rotated order so that the 8 lanes of a quarter warp (rows 128
-            // bytes apart) hit different banks.  (First version: warps 6-7, which delayed their trailing
-            // query rows by the whole K pass.)
-            const int tr = threadIdx.x & 63;
-#pragma unroll 1
-            for (int j = warp >> 1; j < nkv; j += 2) {
-                const bool live = j * BKV + tr < p.T;
-                const float rk = live ? rstd_k[j * BKV + tr] : 0.f;
-                mbar_wait(&k_full[j], 0);
-                if (live) {
-                    uint8_t* rowp = sK + j * KV_TILE_BYTES + tr * 128;
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        uint4* cp = reinterpret_cast<uint4*>(rowp + (((c + lane) & 7) << 4));
-                        const uint4 v = *cp;
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                        uint32_t o[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            o[e] = pack_bf16x2(__uint_as_float(w[e] << 16) * rk, __uint_as_float(w[e] & 0xffff0000u) * rk);
-                        *cp = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
-                }
-                fence_proxy_async_smem();          // generic-proxy writes -> visible to the UMMA reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&k_scaled[j]);
-            }
-        }
         float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
         float l_run = 0.f, l_prev = 0.f;      // running row sum (relative to m_run); previous tile's final sum
 #pragma unroll 1
@@ -473,6 +445,25 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                     for (int c = 0; c < 4; ++c)
                         if (c < nch) tmem_ld_32x32b_x16(t_s + c * 16, s + c * 16);
                     tmem_ld_wait();
+                    if (fused_ln) {
+                        // k_ln's 1/std: one factor per score column (= key row), shared by all query rows
+                        const float4* rk4 = reinterpret_cast<const float4*>(rstd_k + j * BKV);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (c < nch) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float4 rk = rk4[c * 4 + e];
+                                    float a0, a1, a2, a3;
+                                    fmul2(a0, a1, __uint_as_float(s[c * 16 + 4 * e]), __uint_as_float(s[c * 16 + 4 * e + 1]), rk.x, rk.y);
+                                    fmul2(a2, a3, __uint_as_float(s[c * 16 + 4 * e + 2]), __uint_as_float(s[c * 16 + 4 * e + 3]), rk.z, rk.w);
+                                    s[c * 16 + 4 * e] = __float_as_uint(a0);
+                                    s[c * 16 + 4 * e + 1] = __float_as_uint(a1);
+                                    s[c * 16 + 4 * e + 2] = __float_as_uint(a2);
+                                    s[c * 16 + 4 * e + 3] = __float_as_uint(a3);
+                                }
+                            }
+                    }
                     float mx = -INFINITY;
                     if (last) {
                         const int valid = p.T - j * BKV;             // >= 1 valid kv columns in this tile
