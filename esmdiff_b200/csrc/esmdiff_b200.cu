@@ -83,6 +83,7 @@ struct esmdiff_ctx {
                                // B=100, T=258: strided 234 us, runs of 2 / 3 / 6 column tiles 243 / 255 / 290 us, contiguous ranges
                                // 263 us -- re-reading the rotary table row per tile is cheaper than any loss of L2 locality
                                // or balance); ESMDIFF_QKV_RUN overrides
+    int attn_stagger_ns = 0;   // experiment: ESMDIFF_ATTN_STAGGER (attention_resident.cuh)
     bool pdl = true;           // programmatic dependent launch between the kernels of a forward; ESMDIFF_PDL=0 -> off
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
@@ -421,6 +422,7 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     p.ctx = out;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
     p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
+    p.stagger_ns = c->attn_stagger_ns; p.num_sms = c->num_sms;
     if (smem > c->attn_resident_smem) {
         CK(cudaFuncSetAttribute(attn2::attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->attn_resident_smem = smem;
@@ -844,6 +846,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
     if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
+    if (const char* e = getenv("ESMDIFF_ATTN_STAGGER")) c->attn_stagger_ns = atoi(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;
