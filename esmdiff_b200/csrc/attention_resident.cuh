@@ -61,8 +61,6 @@ struct Params {
     const float* qk_sumsq;      // [B*T][2 * nspan]: q spans then k spans (gemm.cuh EPI_QKV_ROPE_LN), or null
     int nspan;                  // D / 128 partial sums per row and operand (<= 12)
     float ln_eps;               // q_ln / k_ln epsilon
-    int stagger_ns;             // experiment (ESMDIFF_ATTN_STAGGER): every second wave of CTAs starts its loads this much later
-    int num_sms;
 };
 
 __host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
@@ -286,9 +284,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            // two CTAs share an SM and would otherwise walk their softmax / MMA phases in lock step
-            // (both waiting for S, then both on the MUFU pipe): offset every second resident CTA
-            if (p.stagger_ns > 0 && ((blockIdx.x / p.num_sms) & 1)) __nanosleep(p.stagger_ns);
             auto load_q = [&](int qt) {
                 uint64_t* bar = &q_full[qt & 1];
                 mbar_arrive_expect_tx(bar, Q_BYTES);

@@ -28,6 +28,19 @@ typedef __nv_bfloat16 bf16;
 
 static std::string g_create_error;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (function, device) -- not to the process (a
+// second device never saw the call) and not to a context (two contexts on one device share it: the
+// one asking for less must not lower it under the other).  Largest value set so far per pair.
+static std::map<std::pair<int, const void*>, int> g_smem_attr;
+template <typename K>
+static cudaError_t ensure_dynamic_smem(int device, K kernel, int bytes) {
+    int& have = g_smem_attr[std::make_pair(device, reinterpret_cast<const void*>(kernel))];
+    if (bytes <= have) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
+
 #define CK(call)                                                                               \
     do {                                                                                       \
         cudaError_t e_ = (call);                                                               \
@@ -83,13 +96,9 @@ struct esmdiff_ctx {
                                // B=100, T=258: strided 234 us, runs of 2 / 3 / 6 column tiles 243 / 255 / 290 us, contiguous ranges
                                // 263 us -- re-reading the rotary table row per tile is cheaper than any loss of L2 locality
                                // or balance); ESMDIFF_QKV_RUN overrides
-    int attn_stagger_ns = 0;   // experiment: ESMDIFF_ATTN_STAGGER (attention_resident.cuh)
     bool pdl = true;           // programmatic dependent launch between the kernels of a forward; ESMDIFF_PDL=0 -> off
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
-    // cudaFuncAttributeMaxDynamicSharedMemorySize is per device: tracked per context, not per process
-    std::set<const void*> smem_attr_set;
-    int attn_resident_smem = 0;
     EncodeTiledFn encode = nullptr;
 
     std::vector<LayerW> layers;
@@ -291,13 +300,7 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     ProfScope prof(c, kind, 2.0 * M * (double)N * K, st);
 #define LAUNCH_GEMM(E, BNV)                                                                    \
     {                                                                                          \
-        const void* fn_ = reinterpret_cast<const void*>(&gemm::gemm_bf16_tn_kernel<E, BNV>);   \
-        if (!c->smem_attr_set.count(fn_)) {                                                    \
-            CK(cudaFuncSetAttribute(gemm::gemm_bf16_tn_kernel<E, BNV>,                         \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize,               \
-                                    gemm::Cfg<E, BNV>::SMEM_BYTES));                           \
-            c->smem_attr_set.insert(fn_);                                                      \
-        }                                                                                      \
+        CK(ensure_dynamic_smem(c->device, gemm::gemm_bf16_tn_kernel<E, BNV>, gemm::Cfg<E, BNV>::SMEM_BYTES));       \
         CK(launch_pdl(c->pdl, gemm::gemm_bf16_tn_kernel<E, BNV>, dim3(grid), dim3(gemm::THREADS),                   \
                       gemm::Cfg<E, BNV>::SMEM_BYTES, st, ta, tb, tc, p));                                           \
     }
@@ -380,11 +383,7 @@ static int launch_attention_streaming(esmdiff_ctx* c, const bf16* qkv, bf16* out
     p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
     const int smem = attn::smem_bytes(T);
     if (smem > 227 * 1024) return c->fail("attention: sequence too long for the shared-memory rstd_k table");
-    const void* fn = reinterpret_cast<const void*>(&attn::attention_fwd_kernel);
-    if (!c->smem_attr_set.count(fn)) {
-        CK(cudaFuncSetAttribute(attn::attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        c->smem_attr_set.insert(fn);
-    }
+    CK(ensure_dynamic_smem(c->device, attn::attention_fwd_kernel, smem));
     const int grid = B * H * p.q_tiles;
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn::DH, st);
     CK(launch_pdl(c->pdl, attn::attention_fwd_kernel, dim3(grid), dim3(attn::THREADS), smem, st, tq, tkv, p));
@@ -422,11 +421,7 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     p.ctx = out;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
     p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
-    p.stagger_ns = c->attn_stagger_ns; p.num_sms = c->num_sms;
-    if (smem > c->attn_resident_smem) {
-        CK(cudaFuncSetAttribute(attn2::attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        c->attn_resident_smem = smem;
-    }
+    CK(ensure_dynamic_smem(c->device, attn2::attention_resident_kernel, smem));
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn2::DH, st);
     CK(launch_pdl(c->pdl, attn2::attention_resident_kernel, dim3(B * H), dim3(attn2::THREADS), smem, st, tq, tkv, tkvt, p));
     c->launches++;
@@ -846,7 +841,6 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
     if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
-    if (const char* e = getenv("ESMDIFF_ATTN_STAGGER")) c->attn_stagger_ns = atoi(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;

@@ -305,6 +305,27 @@ def test_qkv_epilogue_with_qk_layernorm_and_rope(engine, B, T, D):
     check(att, ref2.transpose(1, 2).reshape(M, D), 6e-3, 2.5e-2)
 
 
+def test_two_contexts_on_one_device_share_function_attributes(engine):
+    """The dynamic shared-memory limit of a kernel belongs to (function, device): a second context that
+    needs less must not lower it under the first (seen in round 2: 'invalid argument' at T = 386 after
+    another engine had launched T = 258), and a context must not assume another one raised it."""
+    from esmdiff_b200.engine import Dims, Engine
+    g = torch.Generator(device=DEV).manual_seed(9)
+    H, D = 2, 128
+    big = (torch.randn(514, 3 * D, device=DEV, generator=g)).bfloat16()
+    small = (torch.randn(60, 3 * D, device=DEV, generator=g)).bfloat16()
+    a = engine.op_attention(big, 1, 514, H)
+    other = Engine(Dims(d_model=256, n_heads=4, v_heads=8, n_layers=1))
+    other.op_attention(small, 1, 60, H)
+    other.synchronize()
+    b = engine.op_attention(big, 1, 514, H)                     # larger request again, from the first context
+    c = other.op_attention(big, 1, 514, H)                      # and from the one that only ever asked for less
+    engine.synchronize()
+    other.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    other.close()
+
+
 def test_attention_permutation_property_full_size(engine):
     """softmax attention is equivariant to permuting the keys/values of a sample: at the config-2
     shape (B=63,T=258,H=24), shuffling the kv rows of every sample leaves the output unchanged

@@ -99,8 +99,6 @@ def bench_attn(flush):
         got = e.op_attention(qkv, B, T, H)
         e.synchronize()
         print(f"  attention peaked logits {tag}: rel_fro={((got.float() - ref).norm() / ref.norm()).item():.2e}", flush=True)
-    for st in ("300", "600", "900", "1500"):
-        engs["stagger" + st] = engine(ESMDIFF_ATTN_STAGGER=st)
     for (B, T, H) in [(100, 258, 24), (32, 386, 24), (32, 514, 24), (64, 514, 24), (32, 642, 24), (32, 766, 24), (100, 130, 24)]:
         qkv = torch.randn(B * T, 3 * H * 64, device=dev, generator=g).bfloat16()
         line = f"  attention B={B} T={T} H={H}:"
