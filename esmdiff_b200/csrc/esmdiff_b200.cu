@@ -116,6 +116,39 @@ struct esmdiff_ctx {
     bool finalized = false;
     std::vector<void*> owned;
 
+    // Two workspace sets.  The members below are the ACTIVE set (what the launchers read); activate(i)
+    // swaps them with the parked one.  Launches are enqueued by one host thread and capture their
+    // pointers at enqueue time, so switching between enqueues is safe.  Set 1 exists for the
+    // two-stream sampling loop (esmdiff_ddpm_sample): small batches are split into two independent
+    // halves that run on two streams and fill each other's partial waves.
+    struct WorkspaceSet {
+        int64_t ws_rows = 0;
+        float *x = nullptr, *headh = nullptr, *logits_ws = nullptr, *qk_sumsq = nullptr, *aux_ws = nullptr;
+        float *cond = nullptr, *te_hidden = nullptr;
+        float2* stats = nullptr;
+        bf16 *xn = nullptr, *qkv = nullptr, *att = nullptr, *hbuf = nullptr;
+    };
+    WorkspaceSet parked;
+    int active_ws = 0;
+    void swap_ws() {
+        WorkspaceSet cur;
+        cur.ws_rows = ws_rows; cur.x = x; cur.headh = headh; cur.logits_ws = logits_ws; cur.qk_sumsq = qk_sumsq;
+        cur.aux_ws = aux_ws; cur.cond = cond; cur.te_hidden = te_hidden; cur.stats = stats; cur.xn = xn; cur.qkv = qkv;
+        cur.att = att; cur.hbuf = hbuf;
+        ws_rows = parked.ws_rows; x = parked.x; headh = parked.headh; logits_ws = parked.logits_ws;
+        qk_sumsq = parked.qk_sumsq; aux_ws = parked.aux_ws; cond = parked.cond; te_hidden = parked.te_hidden;
+        stats = parked.stats; xn = parked.xn; qkv = parked.qkv; att = parked.att; hbuf = parked.hbuf;
+        parked = cur;
+        active_ws ^= 1;
+    }
+    int activate(int i) {
+        if (i != active_ws) swap_ws();
+        if (!cond && (alloc(&cond, cfg.d_model) || alloc(&te_hidden, cfg.d_model))) return 1;
+        return 0;
+    }
+    int64_t split_rows = 8192;                 // ESMDIFF_SPLIT_ROWS: batches of at most this many token rows are sampled as two halves
+    cudaStream_t sstream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_sfork = nullptr, ev_sjoin[2] = {nullptr, nullptr};
     // workspace (grows with the largest B*T seen)
     int64_t ws_rows = 0;
     float *x = nullptr, *headh = nullptr, *logits_ws = nullptr;
@@ -139,7 +172,7 @@ struct esmdiff_ctx {
     cudaStream_t gstream = nullptr;            // capture is illegal on the legacy default stream
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     struct GraphRec { cudaGraphExec_t exec = nullptr; int64_t kernels = 0; bool warmed = false; };
-    std::map<std::tuple<int, int, const void*, const void*>, GraphRec> graphs;
+    std::map<std::tuple<int, int, const void*, const void*, int>, GraphRec> graphs;
     void drop_graphs() {
         for (auto& kv : graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -571,7 +604,10 @@ static int forward_step(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
     const int64_t M = (int64_t)B * T;
     const bool want = !c->prof && (c->graph_mode == 1 || (c->graph_mode == -1 && M <= c->graph_max_rows));
     if (!want) return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
-    auto key = std::make_tuple(B, T, (const void*)seq, (const void*)xt);
+    // the library's own (non-default, non-blocking) streams can be captured directly; a caller's stream
+    // may be the legacy default stream, where capture is illegal -> fork to gstream
+    const bool own = st != nullptr && (st == c->sstream[0] || st == c->sstream[1]);
+    auto key = std::make_tuple(B, T, (const void*)seq, (const void*)xt, c->active_ws);
     if (c->graphs.size() > 64 && !c->graphs.count(key)) c->drop_graphs();     // callers that never reuse buffers
     esmdiff_ctx::GraphRec& g = c->graphs[key];
     if (logits != c->logits_ws) return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
@@ -580,16 +616,17 @@ static int forward_step(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
             g.warmed = true;
             return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
         }
-        if (!c->gstream) {
+        if (!own && !c->gstream) {
             CK(cudaStreamCreateWithFlags(&c->gstream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         }
         const int64_t l0 = c->launches;
         cudaGraph_t graph = nullptr;
-        CK(cudaStreamBeginCapture(c->gstream, cudaStreamCaptureModeThreadLocal));
-        const int rc = forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, c->gstream);
-        const cudaError_t e = cudaStreamEndCapture(c->gstream, &graph);
+        cudaStream_t cs = own ? st : c->gstream;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const int rc = forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, cs);
+        const cudaError_t e = cudaStreamEndCapture(cs, &graph);
         g.kernels = c->launches - l0;
         c->launches = l0;                                  // nothing ran yet
         if (rc != 0 || e != cudaSuccess || graph == nullptr) {
@@ -607,24 +644,29 @@ static int forward_step(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
             return forward_impl(c, seq, xt, B, T, c->cond, 0, logits, nullptr, st);
         }
     }
-    CK(cudaEventRecord(c->ev_fork, st));
-    CK(cudaStreamWaitEvent(c->gstream, c->ev_fork, 0));
-    CK(cudaGraphLaunch(g.exec, c->gstream));
-    CK(cudaEventRecord(c->ev_join, c->gstream));
-    CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (own) {
+        CK(cudaGraphLaunch(g.exec, st));
+    } else {
+        CK(cudaEventRecord(c->ev_fork, st));
+        CK(cudaStreamWaitEvent(c->gstream, c->ev_fork, 0));
+        CK(cudaGraphLaunch(g.exec, c->gstream));
+        CK(cudaEventRecord(c->ev_join, c->gstream));
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    }
     c->launches += g.kernels;
     return 0;
 }
 
 template <int MODE>
 static int launch_sampler(esmdiff_ctx* c, const float* logits, const float* u, int64_t* x, float* logp,
-                          int M, float mc_t, float mc_s, uint64_t seed, uint32_t step, cudaStream_t st) {
+                          int M, float mc_t, float mc_s, uint64_t seed, uint32_t step, cudaStream_t st,
+                          uint32_t row_offset = 0) {
     const int V = c->cfg.n_structure_heads;
     if (V > sampler::THREADS * sampler::MAX_PER_THREAD) return c->fail("sampler: vocabulary too large");
     ProfScope prof(c, ESMDIFF_PROF_SAMPLER, (u ? 8.0 : 4.0) * M * V, st);
     sampler::sample_rows_kernel<MODE><<<M, sampler::THREADS, 0, st>>>(
         logits, (long long)V, u, reinterpret_cast<long long*>(x), logp, M, V,
-        ESMDIFF_STRUCTURE_MASK_TOKEN, mc_t, mc_s, (unsigned long long)seed, step);
+        ESMDIFF_STRUCTURE_MASK_TOKEN, mc_t, mc_s, (unsigned long long)seed, step, row_offset);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -841,6 +883,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
     if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
+    if (const char* e = getenv("ESMDIFF_SPLIT_ROWS")) c->split_rows = atoll(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;
@@ -871,6 +914,11 @@ int esmdiff_destroy(esmdiff_ctx* c) {
     cudaDeviceSynchronize();
     c->drop_graphs();
     if (c->gstream) cudaStreamDestroy(c->gstream);
+    for (int i = 0; i < 2; ++i) {
+        if (c->sstream[i]) cudaStreamDestroy(c->sstream[i]);
+        if (c->ev_sjoin[i]) cudaEventDestroy(c->ev_sjoin[i]);
+    }
+    if (c->ev_sfork) cudaEventDestroy(c->ev_sfork);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     for (void* p : c->owned)
@@ -1085,7 +1133,7 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
     if (steps <= 0 || !sigma || !mc_t || !mc_s) return c->fail("ddpm_sample: bad schedule");
     cudaStream_t st = (cudaStream_t)stream;
     const int M = B * T;
-    if (ensure_workspace(c, M)) return 1;
+    if (c->activate(0)) return 1;
     if (prior) {
         CK(cudaMemcpyAsync(out, prior, (size_t)M * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     } else {
@@ -1094,17 +1142,55 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
         c->launches++;
         CK(cudaGetLastError());
     }
-    for (int i = 0; i < steps; ++i) {
-        if (launch_time_embed(c, sigma[i], c->cond, st)) return 1;
-        if (forward_step(c, seq, out, B, T, c->logits_ws, st)) return 1;
-        if (launch_sampler<0>(c, c->logits_ws, nullptr, out, nullptr, M, mc_t[i], mc_s[i], seed, (uint32_t)i, st))
-            return 1;
+    // Samples are independent (the reference repeats one row, sample_esmdiff.py:186), so a small batch
+    // is walked as TWO halves on two streams, each with its own workspace: at a few thousand token rows
+    // every GEMM is one or two waves of tiles on 74 CTA pairs (out_proj at 13 samples: 84 tiles = 2 waves
+    // for 1.14 waves of work) and the attention grid barely exceeds the 296 resident CTAs, so the tail
+    // of each kernel leaves most of the chip idle; with two independent kernel chains in flight the
+    // block scheduler fills those tails with the other half's kernels.  Results are bit-identical to
+    // the single-stream loop (per-row arithmetic does not depend on the batch; the Philox counter uses
+    // the row index of the whole batch).
+    struct Part { int b0, nb; cudaStream_t s; };
+    Part parts[2] = {{0, B, st}, {0, 0, st}};
+    int nparts = 1;
+    if (B >= 2 && M <= c->split_rows && !c->prof) {
+        if (!c->sstream[0]) {
+            for (int i = 0; i < 2; ++i) {
+                CK(cudaStreamCreateWithFlags(&c->sstream[i], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&c->ev_sjoin[i], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreateWithFlags(&c->ev_sfork, cudaEventDisableTiming));
+        }
+        nparts = 2;
+        parts[0] = {0, (B + 1) / 2, c->sstream[0]};
+        parts[1] = {(B + 1) / 2, B - (B + 1) / 2, c->sstream[1]};
+        CK(cudaEventRecord(c->ev_sfork, st));
+        for (int h = 0; h < 2; ++h) CK(cudaStreamWaitEvent(c->sstream[h], c->ev_sfork, 0));
     }
-    if (noise_removal) {
-        if (launch_time_embed(c, sigma[steps], c->cond, st)) return 1;
-        if (forward_step(c, seq, out, B, T, c->logits_ws, st)) return 1;
-        if (launch_sampler<1>(c, c->logits_ws, nullptr, out, nullptr, M, 0.f, 0.f, 0, 0, st)) return 1;
+    const int total = steps + (noise_removal ? 1 : 0);
+    for (int i = 0; i < total; ++i) {               // step-major enqueue: both chains stay fed even without graphs
+        for (int h = 0; h < nparts; ++h) {
+            const Part& pt = parts[h];
+            if (c->activate(h) || ensure_workspace(c, (int64_t)pt.nb * T)) { c->activate(0); return 1; }
+            const int64_t off = (int64_t)pt.b0 * T;
+            int rc = launch_time_embed(c, sigma[i], c->cond, pt.s);
+            rc = rc || forward_step(c, seq + off, out + off, pt.nb, T, c->logits_ws, pt.s);
+            if (!rc) {
+                if (i < steps)
+                    rc = launch_sampler<0>(c, c->logits_ws, nullptr, out + off, nullptr, pt.nb * T, mc_t[i], mc_s[i], seed,
+                                           (uint32_t)i, pt.s, (uint32_t)off);
+                else
+                    rc = launch_sampler<1>(c, c->logits_ws, nullptr, out + off, nullptr, pt.nb * T, 0.f, 0.f, 0, 0, pt.s);
+            }
+            if (rc) { c->activate(0); return 1; }
+        }
     }
+    if (c->activate(0)) return 1;
+    if (nparts == 2)
+        for (int h = 0; h < 2; ++h) {
+            CK(cudaEventRecord(c->ev_sjoin[h], c->sstream[h]));
+            CK(cudaStreamWaitEvent(st, c->ev_sjoin[h], 0));
+        }
     return 0;
 }
 

@@ -78,7 +78,8 @@ template <int MODE>
 __global__ void __launch_bounds__(THREADS)
 sample_rows_kernel(const float* __restrict__ logits, long long ld, const float* __restrict__ u,
                    long long* __restrict__ x, float* __restrict__ out_logp, int M, int V,
-                   int mask_index, float mc_t, float mc_s, unsigned long long seed, uint32_t step) {
+                   int mask_index, float mc_t, float mc_s, unsigned long long seed, uint32_t step,
+                   uint32_t row_offset) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float red[THREADS / 32];
@@ -138,7 +139,7 @@ sample_rows_kernel(const float* __restrict__ logits, long long ld, const float* 
         if (i0 < V) {
             float uu[4] = {0.f, 0.f, 0.f, 0.f};
             if constexpr (MODE == 0) {
-                if (u == nullptr) philox_uniform4(seed, step, row, i0 >> 2, uu);
+                if (u == nullptr) philox_uniform4(seed, step, row + row_offset, i0 >> 2, uu);    // counter = row of the whole batch
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
