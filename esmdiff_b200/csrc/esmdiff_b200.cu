@@ -92,6 +92,10 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    int resid_bn = 0;          // tile width of the residual GEMMs: 0 = per launch (launch_gemm), 192 / 256 forced; ESMDIFF_RESID_BN
+    const void* stats_ptr = nullptr;   // buffer the span below describes (single-kernel entry points)
+    int stats_span = 128;      // columns per partial LayerNorm statistic currently in `stats` (128: embedding kernel and
+                               // 256-wide residual tiles; 96: 192-wide residual tiles)
     int qkv_run = 0;           // tile schedule of the QKV GEMM with the RoPE epilogue (gemm.cuh TileSchedule; measured r2f at
                                // B=100, T=258: strided 234 us, runs of 2 / 3 / 6 column tiles 243 / 255 / 290 us, contiguous ranges
                                // 263 us -- re-reading the rotary table row per tile is cheaper than any loss of L2 locality
@@ -271,6 +275,7 @@ struct GemmLN {                // operands of the LayerNorm-folded epilogues (ge
     const float* colsum = nullptr;
     float2* stats_out = nullptr;
     bf16* xb_out = nullptr;
+    int stats_span = 128;          // columns per partial statistic behind stats_in
     // EPI_QKV_ROPE_LN
     const float* rope = nullptr;
     const float* qk_gamma = nullptr;
@@ -284,10 +289,22 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     if (K % gemm::BK != 0 || K <= 0) return c->fail("gemm: K must be a positive multiple of 64");
     const int max_clusters = c->num_sms / 2;
     const int m_tiles = (M + gemm::BM - 1) / gemm::BM;
-    const int BN = 256;
     const bool is_store = epi == gemm::EPI_STORE_BF16 || epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_QKV_ROPE_LN;
     const bool is_swiglu = epi == gemm::EPI_SWIGLU_BF16 || epi == gemm::EPI_SWIGLU_BF16_LN;
     const bool is_resid = epi == gemm::EPI_RESID_F32 || epi == gemm::EPI_RESID_F32_LN;
+    // Tile width of the residual GEMMs: 256, or 192 when that quantises better on the 74 CTA pairs.  A
+    // 192-wide tile does 3/4 of the work of a 256-wide one at slightly lower efficiency (28 instead of 32
+    // KiB of operands per 384 instead of 512 tensor clocks), so it pays when the wave count does not grow
+    // by 4/3: N = 1536 at 13 samples is 84 tiles = 2 waves against 112 tiles = 2 waves of 3/4 the length.
+    int BN = 256;
+    if (is_resid && N % 192 == 0 && c->resid_bn != 256) {
+        if (c->resid_bn == 192) {
+            BN = 192;
+        } else {
+            const double w256 = ceil((double)m_tiles * (N / 256) / max_clusters), w192 = ceil((double)m_tiles * (N / 192) / max_clusters);
+            if (N % 256 != 0 || w192 * 0.75 * 1.06 < w256) BN = 192;
+        }
+    }
     if ((is_swiglu || is_resid || epi == gemm::EPI_STORE_BF16_LN || epi == gemm::EPI_QKV_ROPE_LN) && N % BN != 0)
         return c->fail("gemm: SwiGLU / residual / LayerNorm-folded epilogues need N % 256 == 0");
     if (epi == gemm::EPI_QKV_ROPE_LN) {
@@ -322,6 +339,7 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     p.out = out; p.ldo = ldo; p.bias = bias; p.scale = scale;
     p.stats_in = ln.stats_in; p.colsum = ln.colsum; p.stats_out = ln.stats_out; p.xb_out = ln.xb_out;
     p.ln_eps = 1e-5f;
+    p.stats_span = ln.stats_span;
     p.rope = ln.rope; p.qk_gamma = ln.qk_gamma; p.qk_sumsq = ln.qk_sumsq; p.T = ln.T; p.n_rope = ln.n_rope;
     p.run = c->qkv_run > 0 && p.n_tiles % c->qkv_run != 0 ? -1 : c->qkv_run;
     const int tiles = p.m_tiles * p.n_tiles;
@@ -339,12 +357,18 @@ static int launch_gemm(esmdiff_ctx* c, int epi, const bf16* A, const bf16* W, in
     }
     switch (epi) {
         case gemm::EPI_STORE_BF16: LAUNCH_GEMM(gemm::EPI_STORE_BF16, 256) break;
-        case gemm::EPI_RESID_F32: LAUNCH_GEMM(gemm::EPI_RESID_F32, 256) break;
+        case gemm::EPI_RESID_F32:
+            if (BN == 192) LAUNCH_GEMM(gemm::EPI_RESID_F32, 192) else LAUNCH_GEMM(gemm::EPI_RESID_F32, 256)
+            break;
         case gemm::EPI_SWIGLU_BF16: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16, 256) break;
         case gemm::EPI_BIAS_GELU_F32: LAUNCH_GEMM(gemm::EPI_BIAS_GELU_F32, 256) break;
         case gemm::EPI_BIAS_F32: LAUNCH_GEMM(gemm::EPI_BIAS_F32, 256) break;
         case gemm::EPI_STORE_BF16_LN: LAUNCH_GEMM(gemm::EPI_STORE_BF16_LN, 256) break;
-        case gemm::EPI_RESID_F32_LN: LAUNCH_GEMM(gemm::EPI_RESID_F32_LN, 256) break;
+        case gemm::EPI_RESID_F32_LN:
+            if (BN == 192) LAUNCH_GEMM(gemm::EPI_RESID_F32_LN, 192) else LAUNCH_GEMM(gemm::EPI_RESID_F32_LN, 256)
+            c->stats_span = BN / 2;            // what the next LayerNorm-folded consumer will find in stats_out
+            c->stats_ptr = ln.stats_out;
+            break;
         case gemm::EPI_SWIGLU_BF16_LN: LAUNCH_GEMM(gemm::EPI_SWIGLU_BF16_LN, 256) break;
         case gemm::EPI_QKV_ROPE_LN: LAUNCH_GEMM(gemm::EPI_QKV_ROPE_LN, 256) break;
         default: return c->fail("gemm: unknown epilogue");
@@ -489,7 +513,7 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
     const int64_t D = c->cfg.d_model, F = c->cfg.ffn_hidden, V = c->cfg.n_structure_heads;
     c->x = nullptr; c->headh = nullptr; c->logits_ws = nullptr;
     c->xn = nullptr; c->qkv = nullptr; c->att = nullptr; c->hbuf = nullptr; c->stats = nullptr; c->qk_sumsq = nullptr;
-    if (c->alloc(&c->stats, M * (D / 128))) return 1;
+    if (c->alloc(&c->stats, M * ((D + 95) / 96))) return 1;      // per-row partials: D/128 or D/96 spans
     if (c->alloc(&c->qk_sumsq, M * 2 * (D / 128))) return 1;
     c->aux_ws = nullptr;
     if (c->cfg.n_aux_out > 0 && c->alloc(&c->aux_ws, M * c->cfg.n_aux_out)) return 1;
@@ -526,6 +550,7 @@ static int run_blocks(esmdiff_ctx* c, int B, int T, cudaStream_t st) {
             make.xb_out = c->xn;
             const bool last = l == c->cfg.n_layers - 1;           // the final norm + head use the LN kernel
             use.colsum = w.cqkv;
+            use.stats_span = c->stats_span;                       // as left by the producer of x (embedding: 128)
             if (c->qk_fused) {
                 // q_ln / k_ln + RoPE inside the QKV epilogue; 1/std of the q and k rows inside attention
                 GemmLN qk = use;
@@ -540,6 +565,7 @@ static int run_blocks(esmdiff_ctx* c, int B, int T, cudaStream_t st) {
             if (launch_gemm(c, gemm::EPI_RESID_F32_LN, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st, make)) return 1;
             // block 0's geometric attention contributes exactly 0 on this path
             use.colsum = w.c1;
+            use.stats_span = c->stats_span;
             if (launch_gemm(c, gemm::EPI_SWIGLU_BF16_LN, c->xn, w.w1, M, 2 * F, D, c->hbuf, F, w.b1, 1.f, st, use)) return 1;
             if (launch_gemm(c, last ? gemm::EPI_RESID_F32 : gemm::EPI_RESID_F32_LN, c->hbuf, w.w2, M, D, F, c->x, D,
                             nullptr, rs, st, make)) return 1;
@@ -582,6 +608,8 @@ static int forward_impl(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, i
                                             c->struct_embed, c->const_vec, aux, aux_stride, c->x, M, D,
                                             c->cfg.seq_vocab, c->cfg.struct_vocab, c->dev_err,
                                             c->ln_fold ? c->xn : nullptr, c->stats);
+    c->stats_span = 128;
+    c->stats_ptr = c->stats;
     }
     c->launches++;
     CK(cudaGetLastError());
@@ -884,6 +912,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
     if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
     if (const char* e = getenv("ESMDIFF_SPLIT_ROWS")) c->split_rows = atoll(e);
+    if (const char* e = getenv("ESMDIFF_RESID_BN")) c->resid_bn = atoi(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;
@@ -1214,6 +1243,8 @@ int esmdiff_decode_structure(esmdiff_ctx* c, const int64_t* tokens, int B, int T
         dec::embed_tokens_kernel<<<(M + 7) / 8, 256, 0, st>>>(reinterpret_cast<const long long*>(tokens), c->dec_embed, c->x,
                                                              c->ln_fold ? c->xn : nullptr, c->stats, M, D,
                                                              c->cfg.struct_vocab, c->dev_err);
+        c->stats_span = 128;
+        c->stats_ptr = c->stats;
     }
     c->launches++;
     CK(cudaGetLastError());
@@ -1330,6 +1361,7 @@ int esmdiff_op_gemm_ln(esmdiff_ctx* c, int epi, const void* a, const void* w, in
     ln.colsum = colsum;
     ln.stats_out = (float2*)stats_out;
     ln.xb_out = (bf16*)xb_out;
+    ln.stats_span = (stats_in != nullptr && stats_in == c->stats_ptr) ? c->stats_span : 128;   // as the producing call left it
     return launch_gemm(c, epi, (const bf16*)a, (const bf16*)w, M, N, K, out, ldo, bias, scale, (cudaStream_t)stream, ln);
 }
 int esmdiff_op_fold_layernorm(esmdiff_ctx* c, const float* w, const float* gamma, const float* beta, void* dst,
@@ -1376,6 +1408,7 @@ int esmdiff_op_gemm_qkv_rope(esmdiff_ctx* c, const void* a, const void* w, int M
     ln.stats_in = (const float2*)stats_in;
     ln.colsum = colsum;
     ln.rope = c->rope_rows; ln.qk_gamma = qk_gamma; ln.qk_sumsq = qk_sumsq; ln.T = T; ln.n_rope = n_rope;
+    ln.stats_span = (stats_in != nullptr && stats_in == c->stats_ptr) ? c->stats_span : 128;
     return launch_gemm(c, gemm::EPI_QKV_ROPE_LN, (const bf16*)a, (const bf16*)w, M, N, K, out, ldo, bias, 1.f,
                        (cudaStream_t)stream, ln);
 }

@@ -84,7 +84,8 @@ constexpr int LN_SPAN = 128;              // columns per partial LayerNorm stati
 // one pipeline stage.
 template <int EPI, int BN> struct Cfg {
     static_assert(BN == 256 || BN == 192, "tile widths instantiated");
-    static_assert(BN == 256, "BN = 192 compiles for the 32-column epilogues only; not instantiated");
+    static_assert(BN == 256 || EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN,
+                  "BN = 192 (N = 1536 as 8 column tiles: finer wave quantisation) is instantiated for the residual epilogues");
     static constexpr int BN_CTA = BN / 2;                 // W rows each CTA loads
     static constexpr int B_BYTES = BN_CTA * BK * 2;       // 16 / 12 KiB
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -114,6 +115,8 @@ struct Params {
     float2* stats_out;         // EPI_RESID_F32_LN: [M][N / 128] partials of the updated rows
     __nv_bfloat16* xb_out;     // EPI_RESID_F32_LN: bf16 copy of the updated rows, [M][N]
     float ln_eps;
+    int stats_span;            // *_LN consumers: columns per partial statistic of the A rows (128, or 96 when the
+                               // producing residual GEMM ran 192-wide tiles)
     // EPI_QKV_ROPE_LN
     const float* rope;         // [>= T][64]: cos(t f_i) i < 32 | sin(t f_i), token position t = row % T
     const float* qk_gamma;     // [n_rope]: q_ln.weight | k_ln.weight
@@ -224,14 +227,14 @@ __device__ __forceinline__ void ld_uniform_smem(float* r, const float* s) {
 // mean = avg(mean_i), M2 = sum M2_i + span * sum (mean_i - mean)^2 (Chan et al.).  Returns
 // rstd and -rstd * mean.
 __device__ __forceinline__ void row_mean_rstd(const float2* st, int nspan, bool ok, float eps, float& rstd,
-                                              float& nrm) {
+                                              float& nrm, int span = LN_SPAN) {
     rstd = 0.f;
     nrm = 0.f;
     if (!ok) return;
-    float4 t[6];
+    float4 t[8];
     float ms = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 8; ++i)
         if (2 * i < nspan) {
             t[i] = __ldg(reinterpret_cast<const float4*>(st) + i);
             ms += t[i].x + t[i].z;
@@ -239,12 +242,12 @@ __device__ __forceinline__ void row_mean_rstd(const float2* st, int nspan, bool 
     const float mean = ms / static_cast<float>(nspan);
     float m2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 8; ++i)
         if (2 * i < nspan) {
             const float d0 = t[i].x - mean, d1 = t[i].z - mean;
-            m2 += (t[i].y + t[i].w) + static_cast<float>(LN_SPAN) * (d0 * d0 + d1 * d1);
+            m2 += (t[i].y + t[i].w) + static_cast<float>(span) * (d0 * d0 + d1 * d1);
         }
-    rstd = rsqrtf(m2 / static_cast<float>(nspan * LN_SPAN) + eps);
+    rstd = rsqrtf(m2 / static_cast<float>(nspan * span) + eps);
     nrm = -rstd * mean;
 }
 
@@ -528,8 +531,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     rot = n0 < p.n_rope;                           // warp-uniform: a q or k column tile
                     const int mt = tile / p.n_tiles;
                     if (mt != stat_mt) {
-                        row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
-                                      row_base + lane < p.M, p.ln_eps, rstd_c, nrm_c);
+                        row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / p.stats_span),
+                                      p.K / p.stats_span, row_base + lane < p.M, p.ln_eps, rstd_c, nrm_c, p.stats_span);
                         stat_mt = mt;
                     }
                     rstd = rstd_c;
@@ -559,8 +562,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         rope_mt = mt;
                     }
                 } else {
-                    row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
-                                  row_base + lane < p.M, p.ln_eps, rstd, nrm);
+                    row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / p.stats_span),
+                                  p.K / p.stats_span, row_base + lane < p.M, p.ln_eps, rstd, nrm, p.stats_span);
                 }
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
@@ -664,8 +667,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 }
             } else if constexpr (EPI == EPI_SWIGLU_BF16_LN) {
                 float rstd, nrm;
-                row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / LN_SPAN), p.K / LN_SPAN,
-                              row_base + lane < p.M, p.ln_eps, rstd, nrm);
+                row_mean_rstd(p.stats_in + static_cast<long long>(row_base + lane) * (p.K / p.stats_span),
+                              p.K / p.stats_span, row_base + lane < p.M, p.ln_eps, rstd, nrm, p.stats_span);
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
                 const uint32_t t_gate = tmem_base + acc * ACC_STRIDE + half * 64 + (static_cast<uint32_t>(q * 32) << 16);
@@ -719,8 +722,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 // count.  Loads run two chunks ahead in two register sets; the first two chunks of
                 // the NEXT tile are requested while this tile drains.  acc / scale is evaluated as
                 // acc * (1 / scale): <= 1 ulp(fp32) from the reference's division.
-                constexpr int NCH = (BN / 2) / 32;
-                static_assert(NCH == 4, "two alternating register sets need an even chunk count");
+                constexpr int NCH = (BN / 2) / 32;          // 4 chunks (BN = 256) or 3 (BN = 192) of 32 columns per warp
+                constexpr int SPAN = BN / 2;                // columns per partial LayerNorm statistic this warp leaves
                 float* xg = reinterpret_cast<float*>(p.out);
                 const float inv = 1.0f / p.scale;
                 const int grp = lane >> 3, qd = lane & 7;                  // rows 8 grp .. 8 grp + 7, column quad qd
@@ -738,7 +741,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         if (k < nr) ld_quad(xr + 4 * k, src + static_cast<long long>(k) * p.ldo);
                 };
                 const int nr = rows_left(tile);
-                if (it == 0) {                          // first tile of this CTA pair: nothing prefetched yet
+                // x loads run two chunks ahead in two register sets.  With an even chunk count the sets
+                // line up across tiles and the first two chunks of the NEXT tile are requested while this
+                // one drains; with three chunks (BN = 192) they would swap roles every tile, so each
+                // tile requests its own first two chunks before it waits for the accumulator instead.
+                constexpr bool CROSS = NCH % 2 == 0;
+                if (!CROSS || it == 0) {
                     ld_chunk(xres, tile, 0);
                     ld_chunk(xres + 32, tile, 1);
                 }
@@ -746,19 +754,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 mbar_wait(&tfull[acc], acc_phase);
                 tcgen05_fence_after();
                 // EPI_RESID_F32_LN: (sum, sum of squares) of my 4 columns of each of the 8 rows, over
-                // the warp's four chunks.  Plain sums over a 128-column span: M2 = q - s^2/128 loses
+                // the warp's chunks.  Plain sums over a SPAN-column span: M2 = q - s^2/SPAN loses
                 // ~1e-7 (1 + (span mean / span std)^2) relative, harmless for a residual stream whose
                 // span means are of the order of its spread; the spans are then combined exactly
                 // (Chan) by the consumer.
                 float st_s[8], st_q[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { st_s[k] = 0.f; st_q[k] = 0.f; }
-#pragma unroll 1
-                for (int c2 = 0; c2 < NCH; c2 += 2)
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = c2 + cc;
-                    float* xr = cc ? xres + 32 : xres;
+                auto do_chunk = [&](const int c, float* xr) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(t_row + c * 32, v);
                     tmem_ld_wait();
@@ -783,7 +786,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         }
                     }
                     if (c + 2 < NCH) ld_chunk(xr, tile, c + 2);
-                    else if (nt < num_tiles) ld_chunk(xr, nt, c + 2 - NCH);
+                    else if (CROSS && nt < num_tiles) ld_chunk(xr, nt, c + 2 - NCH);
+                };
+                if constexpr (NCH == 4) {
+#pragma unroll 1
+                    for (int c2 = 0; c2 < NCH; c2 += 2) {
+                        do_chunk(c2, xres);
+                        do_chunk(c2 + 1, xres + 32);
+                    }
+                } else {
+                    do_chunk(0, xres);
+                    do_chunk(1, xres + 32);
+                    do_chunk(2, xres);
                 }
                 if constexpr (EPI == EPI_RESID_F32_LN) {
                     // add the 8 column quads of each row: 8 items over 8 lanes -> lane qd ends with row qd
@@ -806,8 +820,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         if (qd == k) { my_s = st_s[k]; my_q = st_q[k]; }
                     if (qd < nr) {
                         const long long row = static_cast<long long>(row_base + grp * 8 + qd);
-                        const float sm = my_s * (1.0f / LN_SPAN);
-                        p.stats_out[row * (p.N / LN_SPAN) + nb * (BN / LN_SPAN) + half] = make_float2(sm, my_q - my_s * sm);
+                        const float sm = my_s * (1.0f / SPAN);
+                        p.stats_out[row * (p.N / SPAN) + nb * 2 + half] = make_float2(sm, my_q - my_s * sm);
                     }
                 }
             } else {

@@ -177,6 +177,65 @@ def test_gemm_layernorm_folded_epilogues(engine, M, D, F_h):
     assert rel_fro(qkv, ln @ wq.T) < 1.5 * rel_fro(qkv2, ln @ wq.T) + 1e-4
 
 
+@pytest.mark.parametrize("M", [3354, 1000, 130, 25800])
+def test_residual_gemm_192_wide_tiles(M):
+    """The residual GEMMs can run 192-wide tiles (N = 1536 as 8 column tiles: 84 -> 112 tiles of 3/4 the
+    length at 13 samples, 2 waves either way); the statistics they leave are then per 96 columns and the
+    LayerNorm-folded consumers combine 16 spans instead of 12.  Same checks as the 256-wide form, plus
+    bit-equality of the updated stream between the two tile widths (same MMA order along K)."""
+    import os
+    from esmdiff_b200.engine import Dims, Engine
+    engs = {}
+    for bn in ("256", "192"):
+        os.environ["ESMDIFF_RESID_BN"] = bn
+        try:
+            engs[bn] = Engine(Dims())
+        finally:
+            os.environ.pop("ESMDIFF_RESID_BN")
+    g = torch.Generator(device=DEV).manual_seed(21)
+    D, F_h = 1536, 4096
+    a = torch.randn(M, D, device=DEV, generator=g).bfloat16()
+    wo = (torch.randn(D, D, device=DEV, generator=g) / D ** 0.5).bfloat16()
+    h = torch.randn(M, F_h, device=DEV, generator=g).bfloat16()
+    w2 = (torch.randn(D, F_h, device=DEV, generator=g) / F_h ** 0.5).bfloat16()
+    x0 = torch.randn(M, D, device=DEV, generator=g) * 3 + 0.7
+    x0[:, 77] += 900.0
+    gamma = 1.0 + 0.3 * torch.randn(D, device=DEV, generator=g)
+    beta = 0.2 * torch.randn(D, device=DEV, generator=g)
+    wq = torch.randn(3 * D, D, device=DEV, generator=g) / D ** 0.5
+    res = {}
+    for bn, eng in engs.items():
+        x = x0.clone()
+        xb = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+        stats = torch.zeros(M, 16, 2, device=DEV)
+        eng.op_gemm_ln(6, a, wo, x, scale=1.1547005, stats_out=stats, xb_out=xb)        # out_proj: K = 1536
+        eng.op_gemm_ln(6, h, w2, x, scale=1.1547005, stats_out=stats, xb_out=xb)        # W2: K = 4096
+        eng.synchronize()
+        ref_x = x0 + (a.float() @ wo.float().T) / 1.1547005 + (h.float() @ w2.float().T) / 1.1547005
+        check(x, ref_x, 2e-5)
+        assert torch.equal(xb, x.bfloat16())
+        span = 96 if bn == "192" else 128
+        st = stats[:, : D // span]
+        mean_i, m2_i = st[..., 0].double(), st[..., 1].double()
+        mean = mean_i.mean(-1)
+        var = (m2_i.sum(-1) + span * ((mean_i - mean[:, None]) ** 2).sum(-1)) / D
+        assert float((mean - x.double().mean(-1)).abs().max()) < 1e-4
+        ref_var = x.double().var(-1, unbiased=False)
+        assert float(((var - ref_var).abs() / ref_var).max()) < 1e-5
+        wq_f, cq, bq = eng.op_fold_layernorm(wq, gamma, beta)
+        qkv = torch.empty(M, 3 * D, dtype=torch.bfloat16, device=DEV)
+        eng.op_gemm_ln(5, xb, wq_f, qkv, bias=bq, stats_in=stats, colsum=cq)             # consumer reads the producer's spans
+        plain = x0.clone()
+        eng.op_gemm(1, a, wo, plain, scale=1.1547005)                                   # residual epilogue without statistics
+        eng.synchronize()
+        check(qkv, F.layer_norm(x, (D,), gamma, beta, 1e-5) @ wq.T, 6e-3, 3e-2)
+        res[bn] = (x, qkv, plain)
+    assert torch.equal(res["256"][0], res["192"][0]) and torch.equal(res["256"][2], res["192"][2])
+    assert rel_fro(res["192"][1], res["256"][1]) < 3e-3
+    for eng in engs.values():
+        eng.close()
+
+
 def test_residual_epilogue_statistics_with_large_row_offset(engine):
     """The residual epilogue accumulates plain (sum, sum of squares) per 128-column span; the claimed
     loss is ~1e-7 (1 + (mean/std)^2) relative.  Pin it at mean/std = 50 (far beyond a LayerNorm

@@ -43,8 +43,8 @@ def engine(**env):
 
 def bench_gemm(flush):
     g = torch.Generator(device="cuda").manual_seed(4)
-    engs = {"auto": engine()}
-    for M in (16254, 9546, 25800):
+    engs = {"auto": engine(), "bn256": engine(ESMDIFF_RESID_BN="256"), "bn192": engine(ESMDIFF_RESID_BN="192")}
+    for M in (25800, 3354, 3096, 12900, 6450):
         for (N, K, epi, name) in [(4608, 1536, 0, "qkv"), (1536, 1536, 1, "out_proj"), (8192, 1536, 2, "w1_swiglu"),
                                   (1536, 4096, 1, "w2")]:
             a = torch.randn(M, K, device=dev, generator=g).bfloat16()
