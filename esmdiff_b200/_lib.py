@@ -99,6 +99,7 @@ _SIGS = {
     "esmdiff_op_attention": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "esmdiff_op_convert_bf16": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "esmdiff_set_time_conditioning": (C.c_int, [_P, C.c_int]),
+    "esmdiff_op_stats_span": (C.c_int, [_P]),
     "esmdiff_decode_structure": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "esmdiff_op_fold_layernorm_centered": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64,
                                                      C.c_int64, C.c_int64, _P]),

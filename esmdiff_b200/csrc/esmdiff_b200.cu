@@ -1432,6 +1432,7 @@ int esmdiff_op_fold_layernorm_centered(esmdiff_ctx* c, const float* w, const flo
     if (cm) CK(cudaFreeAsync(cm, (cudaStream_t)stream));
     return 0;
 }
+int esmdiff_op_stats_span(const esmdiff_ctx* c) { return c ? c->stats_span : 0; }
 int esmdiff_set_time_conditioning(esmdiff_ctx* c, int on) {
     if (!c) return 1;
     c->cfg.time_conditioning = on ? 1 : 0;

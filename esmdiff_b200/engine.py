@@ -278,6 +278,11 @@ class Engine:
                                               _ptr(colsum), _ptr(stats_out), _ptr(xb_out), _stream()))
         return out
 
+    @property
+    def stats_span(self) -> int:
+        """Columns per partial LayerNorm statistic the last residual+statistics GEMM (epilogue 6) wrote."""
+        return int(self.L.esmdiff_op_stats_span(self.h))
+
     def op_fold_layernorm(self, w, gamma, beta=None, swiglu_hidden=0, center_rows=0, center_block=1):
         """center_rows > 0: column means of each block of ``center_block`` rows are removed from the
         first ``center_rows`` rows first (q_ln / k_ln centring folded into the QKV weight)."""

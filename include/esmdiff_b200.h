@@ -169,8 +169,13 @@ int esmdiff_op_gemm(esmdiff_ctx* ctx, int epilogue, const void* a_bf16_dev, cons
 /* The LayerNorm-folded epilogues (the block pre-LNs of esm UnifiedTransformerBlock, applied as
  * LN(x) W^T = rstd (x (gamma.W)^T - mean colsum(gamma.W)) + beta W^T):
  *   5 store bf16 with row statistics, 6 resid fp32 + bf16 copy of the new rows (xb_out [M,N]) +
- *   partial statistics (stats_out, float2 [M, N/128]), 7 SwiGLU bf16 with row statistics.
- *   stats_in: float2 [M, K/128] (mean, M2) per 128-column span of the A rows; colsum/bias: [N]. */
+ *   partial statistics (stats_out), 7 SwiGLU bf16 with row statistics.
+ *   stats_out: float2, CAPACITY [M, N/96]: (mean, M2) per span of the updated rows, densely packed with
+ *   N/span entries per row, span = 128 or -- when the library runs the residual GEMM with 192-wide tiles
+ *   (finer wave quantisation, chosen per launch) -- 96; esmdiff_op_stats_span() tells which after the
+ *   call, and a consumer call given the same pointer as stats_in uses it automatically.
+ *   stats_in: such a buffer (any other pointer is taken as 128-column spans, float2 [M, K/128]);
+ *   colsum/bias: [N]. */
 int esmdiff_op_gemm_ln(esmdiff_ctx* ctx, int epilogue, const void* a_bf16_dev, const void* w_bf16_dev,
                        int M, int N, int K, void* out_dev, int64_t ldo, const float* bias_dev,
                        float scale, const void* stats_in_dev, const float* colsum_dev,
@@ -200,6 +205,7 @@ int esmdiff_op_attention(esmdiff_ctx* ctx, const void* qkv_bf16_dev, void* ctx_b
  *     qk_sumsq_out fp32 [M, n_rope/128]: sum of y^2 over each 128-column span;
  *   - esmdiff_op_attention_ln: attention on that layout; 1/sqrt(mean y^2 + eps) of the q and k rows
  *     is applied inside (qk_sumsq [B*T, 2*H*64/128]: q spans then k spans). */
+int esmdiff_op_stats_span(const esmdiff_ctx* ctx);   /* span of the statistics the last epilogue-6 call left */
 int esmdiff_op_fold_layernorm_centered(esmdiff_ctx* ctx, const float* w_dev, const float* gamma_dev,
                                        const float* beta_dev, void* dst_bf16_dev, float* colsum_dev,
                                        float* bias_dev, int64_t rows, int64_t cols, int64_t center_rows,

@@ -117,11 +117,14 @@ def test_gemm_linearity_full_size(engine):
     check(once, (a.float() @ w.float().T) / 2.0, 2e-5)
 
 
-def _combine_stats(stats, D):
-    """(mean, M2) partials over 128-column spans -> row mean, biased variance (Chan et al.)."""
-    mean_i, m2_i = stats[..., 0].double(), stats[..., 1].double()
+def _combine_stats(stats, D, span=128):
+    """(mean, M2) partials over `span`-column spans (densely packed, D / span per row) -> row mean,
+    biased variance (Chan et al.)."""
+    M = stats.shape[0]
+    st = stats.reshape(M, -1)[:, : 2 * (D // span)].reshape(M, D // span, 2)
+    mean_i, m2_i = st[..., 0].double(), st[..., 1].double()
     mean = mean_i.mean(-1)
-    m2 = m2_i.sum(-1) + 128.0 * ((mean_i - mean[:, None]) ** 2).sum(-1)
+    m2 = m2_i.sum(-1) + float(span) * ((mean_i - mean[:, None]) ** 2).sum(-1)
     return mean, m2 / D
 
 
@@ -139,13 +142,13 @@ def test_gemm_layernorm_folded_epilogues(engine, M, D, F_h):
     x0[::7] -= 2.5                                               # row-dependent mean
     x = x0.clone()
     xb = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
-    stats = torch.zeros(M, D // 128, 2, device=DEV)
+    stats = torch.zeros(M, (D + 95) // 96, 2, device=DEV)         # capacity for either span (include/esmdiff_b200.h)
     engine.op_gemm_ln(6, a, wo, x, scale=1.1547005, stats_out=stats, xb_out=xb)
     engine.synchronize()
     ref_x = x0 + (a.float() @ wo.float().T) / 1.1547005
     check(x, ref_x, 2e-5)
     assert torch.equal(xb, x.bfloat16())                         # the copy is the rounded new stream
-    mean, var = _combine_stats(stats, D)
+    mean, var = _combine_stats(stats, D, engine.stats_span)
     assert float((mean - x.double().mean(-1)).abs().max()) < 1e-4
     ref_var = x.double().var(-1, unbiased=False)
     assert float(((var - ref_var).abs() / ref_var).max()) < 1e-5
@@ -214,11 +217,8 @@ def test_residual_gemm_192_wide_tiles(M):
         ref_x = x0 + (a.float() @ wo.float().T) / 1.1547005 + (h.float() @ w2.float().T) / 1.1547005
         check(x, ref_x, 2e-5)
         assert torch.equal(xb, x.bfloat16())
-        span = 96 if bn == "192" else 128
-        st = stats[:, : D // span]
-        mean_i, m2_i = st[..., 0].double(), st[..., 1].double()
-        mean = mean_i.mean(-1)
-        var = (m2_i.sum(-1) + span * ((mean_i - mean[:, None]) ** 2).sum(-1)) / D
+        assert eng.stats_span == (96 if bn == "192" else 128)
+        mean, var = _combine_stats(stats, D, eng.stats_span)
         assert float((mean - x.double().mean(-1)).abs().max()) < 1e-4
         ref_var = x.double().var(-1, unbiased=False)
         assert float(((var - ref_var).abs() / ref_var).max()) < 1e-5
@@ -247,11 +247,11 @@ def test_residual_epilogue_statistics_with_large_row_offset(engine):
     x0 = 50.0 + torch.randn(M, D, device=DEV, generator=g)
     x = x0.clone()
     xb = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
-    stats = torch.zeros(M, D // 128, 2, device=DEV)
+    stats = torch.zeros(M, (D + 95) // 96, 2, device=DEV)
     engine.op_gemm_ln(6, a, wo, x, scale=1.0, stats_out=stats, xb_out=xb)
     engine.synchronize()
     assert torch.equal(x, x0)
-    mean, var = _combine_stats(stats, D)
+    mean, var = _combine_stats(stats, D, engine.stats_span)
     ref_var = x0.double().var(-1, unbiased=False)
     assert float((mean - x0.double().mean(-1)).abs().max()) < 1e-4
     assert float(((var - ref_var).abs() / ref_var).max()) < 1e-3

@@ -28,7 +28,7 @@ ones = torch.ones(1536, device=dev)
 wq_f, cq, bq = e.op_fold_layernorm(wq.float(), ones, ones)
 w1_f, c1, b1 = e.op_fold_layernorm(w1.float(), ones, ones, swiglu_hidden=4096)
 xb = torch.empty(M, 1536, dtype=torch.bfloat16, device=dev)
-stats = torch.zeros(M, 12, 2, device=dev)
+stats = torch.zeros(M, 16, 2, device=dev)
 att0 = torch.randn(M, 1536, device=dev, generator=g).bfloat16()
 e.op_gemm_ln(6, att0, wo, x, scale=1.1547, stats_out=stats, xb_out=xb)      # fills xb / stats
 e.synchronize()

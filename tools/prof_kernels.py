@@ -37,7 +37,7 @@ w1f, c1, b1 = e.op_fold_layernorm(w1, ones, None, swiglu_hidden=F)
 att = torch.randn(M, D, device=dev, generator=g).bfloat16()
 hb = torch.randn(M, F, device=dev, generator=g).bfloat16()
 xr = x.clone()
-st2 = torch.zeros(M, D // 128, 2, device=dev)
+st2 = torch.zeros(M, 16, 2, device=dev)          # capacity for 96- or 128-column spans
 xb2 = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
 hout = torch.empty(M, F, dtype=torch.bfloat16, device=dev)
 for rep in range(2):
