@@ -121,7 +121,7 @@ def _combine_stats(stats, D, span=128):
     """(mean, M2) partials over `span`-column spans (densely packed, D / span per row) -> row mean,
     biased variance (Chan et al.)."""
     M = stats.shape[0]
-    st = stats.reshape(M, -1)[:, : 2 * (D // span)].reshape(M, D // span, 2)
+    st = stats.reshape(-1)[: M * (D // span) * 2].reshape(M, D // span, 2)      # dense: D / span entries per row
     mean_i, m2_i = st[..., 0].double(), st[..., 1].double()
     mean = mean_i.mean(-1)
     m2 = m2_i.sum(-1) + float(span) * ((mean_i - mean[:, None]) ** 2).sum(-1)
