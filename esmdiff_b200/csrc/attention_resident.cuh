@@ -53,6 +53,10 @@ struct Params {
     int B, T, H;
     int nq;                     // query tiles of 128 rows on the tensor path: ceil(T / 128), or floor when n_left > 0
     int n_left;                 // 0..MAX_LEFT trailing query rows done by warps 6-7 on CUDA cores
+    int q_splits;               // CTAs per (sample, head): each takes a contiguous range of the query tiles (the last one
+                                // also the trailing rows) and loads K/V for itself.  2 when the grid would otherwise be
+                                // just over a multiple of the resident CTA count (13 samples: 312 CTAs on 296 slots = two
+                                // rounds for 1.05 rounds of work; 624 half-length CTAs = three rounds of 0.55)
     int nkv;                    // ceil(T / 64)
     int tail_cols;              // width of the last kv tile: multiple of 16 in [16, 64]
     const __nv_bfloat16* qkv;   // [B*T, 3*H*64] (the leftover warps read their query rows directly)
@@ -196,11 +200,14 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int h = blockIdx.x % p.H;
-    const int b = blockIdx.x / p.H;
+    const int split = blockIdx.x % p.q_splits;
+    const int h = (blockIdx.x / p.q_splits) % p.H;
+    const int b = blockIdx.x / (p.q_splits * p.H);
     const int D = p.H * DH;
     const int row0 = b * p.T;
-    const int nq = p.nq, nkv = p.nkv;
+    const int qt0 = split * p.nq / p.q_splits;                            // first query tile of this CTA
+    const int nq = (split + 1) * p.nq / p.q_splits - qt0, nkv = p.nkv;   // its query tiles
+    const int n_left = split == p.q_splits - 1 ? p.n_left : 0;           // trailing rows go with the last range
     const int nsteps = nq * nkv;
     const bool fused_ln = p.qk_sumsq != nullptr;
     uint64_t* k_ready = k_full;                           // K tiles are consumed as the TMA loads leave them
@@ -287,7 +294,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
             auto load_q = [&](int qt) {
                 uint64_t* bar = &q_full[qt & 1];
                 mbar_arrive_expect_tx(bar, Q_BYTES);
-                tma_load_2d(sQ + (qt & 1) * Q_BYTES, &tmQ, bar, h * DH, row0 + qt * BQ);
+                tma_load_2d(sQ + (qt & 1) * Q_BYTES, &tmQ, bar, h * DH, row0 + (qt0 + qt) * BQ);
             };
             auto load_kv = [&](uint8_t* dst, uint64_t* bar, int col, int j) {
                 const bool last = j == nkv - 1;
@@ -374,7 +381,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     } else if (warp >= 6) {
         // ===================== trailing query rows past the last full tile =====================
         const int lw = warp - 6;
-        if (lw < p.n_left) {
+        if (lw < n_left) {
             const int t = p.nq * BQ + lw;
             float sc = p.scale_log2;
             if (fused_ln) sc *= rstd_q[t];
@@ -393,9 +400,9 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         auto epilogue = [&](int qt, float l) {
             mbar_wait(o_full, qt & 1);
             tcgen05_fence_after();
-            if (qt * BQ + warp * 32 < p.T) {
+            if ((qt0 + qt) * BQ + warp * 32 < p.T) {
                 const float inv = 1.0f / l;
-                const int t = qt * BQ + r;
+                const int t = (qt0 + qt) * BQ + r;
                 uint4* dst = reinterpret_cast<uint4*>(p.ctx + static_cast<long long>(row0 + t) * D + h * DH);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -422,7 +429,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         float l_run = 0.f, l_prev = 0.f;      // running row sum (relative to m_run); previous tile's final sum
 #pragma unroll 1
         for (int qt = 0; qt < nq; ++qt) {
-            const bool active = qt * BQ + warp * 32 < p.T;           // warp-uniform
+            const bool active = (qt0 + qt) * BQ + warp * 32 < p.T;   // warp-uniform
             for (int j = 0; j < nkv; ++j) {
                 const int i = qt * nkv + j;
                 const uint32_t t_s = tmem_base + lane_addr + (i & 1) * BKV;
@@ -430,7 +437,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                     l_prev = l_run;
                     l_run = 0.f;
                     if (fused_ln) {
-                        const int t = qt * BQ + r;
+                        const int t = (qt0 + qt) * BQ + r;
                         sc = p.scale_log2 * (t < p.T ? rstd_q[t] : 1.0f);
                         thresh = RESCALE_LOG2 / sc;
                     }

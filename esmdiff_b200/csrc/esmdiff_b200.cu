@@ -92,6 +92,7 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    int attn_qsplit = 0;       // query-range split of the resident attention: 0 = per launch, 1 / 2 forced; ESMDIFF_ATTN_QSPLIT
     int resid_bn = 0;          // tile width of the residual GEMMs: 0 = per launch (launch_gemm), 192 / 256 forced; ESMDIFF_RESID_BN
     const void* stats_ptr = nullptr;   // buffer the span below describes (single-kernel entry points)
     int stats_span = 128;      // columns per partial LayerNorm statistic currently in `stats` (128: embedding kernel and
@@ -150,7 +151,9 @@ struct esmdiff_ctx {
         if (!cond && (alloc(&cond, cfg.d_model) || alloc(&te_hidden, cfg.d_model))) return 1;
         return 0;
     }
-    int64_t split_rows = 8192;                 // ESMDIFF_SPLIT_ROWS: batches of at most this many token rows are sampled as two halves
+    int64_t split_rows = 0;                    // ESMDIFF_SPLIT_ROWS: batches of at most this many token rows are sampled as two halves
+                                               // (off by default: measured +1.2 % at 13 samples with 256-wide residual tiles, -2 % against
+                                               // the 192-wide ones -- the chip is power-capped even there, so filling idle SMs buys clocks down)
     cudaStream_t sstream[2] = {nullptr, nullptr};
     cudaEvent_t ev_sfork = nullptr, ev_sjoin[2] = {nullptr, nullptr};
     // workspace (grows with the largest B*T seen)
@@ -479,8 +482,17 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     p.scale_log2 = 0.125f * 1.4426950408889634f;
     p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
     CK(ensure_dynamic_smem(c->device, attn2::attention_resident_kernel, smem));
+    // query-range split (attention_resident.cuh Params::q_splits): two half-length CTAs per (sample, head)
+    // when that needs fewer rounds of the 2 x num_sms resident CTAs (each half reloads K/V: ~10 % extra)
+    p.q_splits = 1;
+    if (p.nq >= 2 && c->attn_qsplit != 1) {
+        const double slots = 2.0 * c->num_sms, items = (double)B * H;
+        const double r1 = ceil(items / slots), r2 = ceil(2.0 * items / slots) * 0.55;
+        if (c->attn_qsplit == 2 || r2 < r1 * 0.97) p.q_splits = 2;
+    }
     ProfScope prof(c, ESMDIFF_PROF_ATTENTION, 4.0 * B * H * (double)T * T * attn2::DH, st);
-    CK(launch_pdl(c->pdl, attn2::attention_resident_kernel, dim3(B * H), dim3(attn2::THREADS), smem, st, tq, tkv, tkvt, p));
+    CK(launch_pdl(c->pdl, attn2::attention_resident_kernel, dim3(B * H * p.q_splits), dim3(attn2::THREADS), smem, st, tq,
+                  tkv, tkvt, p));
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -913,6 +925,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
     if (const char* e = getenv("ESMDIFF_SPLIT_ROWS")) c->split_rows = atoll(e);
     if (const char* e = getenv("ESMDIFF_RESID_BN")) c->resid_bn = atoi(e);
+    if (const char* e = getenv("ESMDIFF_ATTN_QSPLIT")) c->attn_qsplit = atoi(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;

@@ -364,6 +364,32 @@ def test_qkv_epilogue_with_qk_layernorm_and_rope(engine, B, T, D):
     check(att, ref2.transpose(1, 2).reshape(M, D), 6e-3, 2.5e-2)
 
 
+@pytest.mark.parametrize("B,T,H", [(13, 258, 24), (2, 514, 4), (1, 642, 2), (3, 130, 4)])
+def test_attention_query_range_split_is_bit_identical(B, T, H):
+    """Two CTAs per (sample, head), each walking half of the query tiles (chosen per launch when the grid
+    is just over a multiple of the resident CTA count), must give exactly the one-CTA result: a query
+    row's arithmetic does not depend on which CTA owns it."""
+    import os
+    from esmdiff_b200.engine import Dims, Engine
+    g = torch.Generator(device=DEV).manual_seed(31)
+    D = H * 64
+    qkv = (torch.randn(B * T, 3 * D, device=DEV, generator=g) * 1.5).bfloat16()
+    sumsq = (torch.rand(B * T, 2 * D // 128, device=DEV, generator=g) + 0.5) * 128
+    outs = []
+    for mode in ("1", "2"):
+        os.environ["ESMDIFF_ATTN_QSPLIT"] = mode
+        try:
+            eng = Engine(Dims(d_model=256, n_heads=4, v_heads=8, n_layers=1))
+        finally:
+            os.environ.pop("ESMDIFF_ATTN_QSPLIT")
+        outs.append((eng.op_attention(qkv, B, T, H), eng.op_attention(qkv, B, T, H, qk_sumsq=sumsq)))
+        eng.synchronize()
+        eng.close()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    q, k, v = [z.view(B, T, H, 64).transpose(1, 2) for z in qkv.float().chunk(3, -1)]
+    check(outs[1][0], F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, D), 5e-3, 2e-2)
+
+
 def test_two_contexts_on_one_device_share_function_attributes(engine):
     """The dynamic shared-memory limit of a kernel belongs to (function, device): a second context that
     needs less must not lower it under the first (seen in round 2: 'invalid argument' at T = 386 after

@@ -450,8 +450,8 @@ def test_cuda_graph_replay_matches_eager_launches():
 
 
 def test_two_stream_half_batches_are_bit_identical():
-    """Small batches are sampled as two independent halves on two streams with two workspaces
-    (esmdiff_ddpm_sample; fills the partial tile waves of small GEMMs).  Per-row arithmetic does not
+    """ESMDIFF_SPLIT_ROWS (off by default): small batches sampled as two independent halves on two
+    streams with two workspaces (esmdiff_ddpm_sample; fills the partial tile waves of small GEMMs).  Per-row arithmetic does not
     depend on the batch and the Philox counter uses the row index of the whole batch, so the tokens
     must equal the single-stream loop's bit for bit -- with and without CUDA graphs, with a prior,
     for odd and even batch sizes, and across repeated calls (workspace / graph reuse)."""
@@ -462,7 +462,8 @@ def test_two_stream_half_batches_are_bit_identical():
     net, emb = esm3_ref.build_reference_model(esm3_ref.Esm3Dims(**TINY), seed=0)
     sd = esm3_ref.full_state_dict(net, emb)
     outs = {}
-    for mode, env in (("single", {"ESMDIFF_SPLIT_ROWS": "0"}), ("split", {}), ("split_eager", {"ESMDIFF_GRAPH": "0"})):
+    for mode, env in (("single", {"ESMDIFF_SPLIT_ROWS": "0"}), ("split", {"ESMDIFF_SPLIT_ROWS": "100000"}),
+                      ("split_eager", {"ESMDIFF_SPLIT_ROWS": "100000", "ESMDIFF_GRAPH": "0"})):
         os.environ.update(env)
         try:
             eng = Engine(Dims(**TINY))
