@@ -92,7 +92,9 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
-    int attn_qsplit = 0;       // query-range split of the resident attention: 0 = per launch, 1 / 2 forced; ESMDIFF_ATTN_QSPLIT
+    int attn_qsplit = 1;       // query-range split of the resident attention: 1 = off (default: measured no gain at 13 samples --
+                               // the 16 CTAs of the second round run alone on their SMs and finish in half the time anyway),
+                               // 0 = decide per launch, 2 = always; ESMDIFF_ATTN_QSPLIT
     int resid_bn = 0;          // tile width of the residual GEMMs: 0 = per launch (launch_gemm), 192 / 256 forced; ESMDIFF_RESID_BN
     const void* stats_ptr = nullptr;   // buffer the span below describes (single-kernel entry points)
     int stats_span = 128;      // columns per partial LayerNorm statistic currently in `stats` (128: embedding kernel and
