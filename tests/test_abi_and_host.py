@@ -224,6 +224,25 @@ def test_checkpoint_config_discovery_and_composed_config(tmp_path, layout):
     assert cu.load_model_cfg(lone)["noise_removal"] is True
 
 
+def test_pdb_writer_layout():
+    """decoder.pdb_model_lines: fixed-column ATOM records as biotite / the reference's targets write them
+    (data/targets/bpti/bpti.pdb), atoms with NaN coordinates left out, TER after the last atom; the
+    multi-MODEL assembly is merge_pdbfiles' (eval_utils.py:437-492)."""
+    from esmdiff_b200.decoder import pdb_model_lines
+    bb = np.arange(2 * 9, dtype=np.float32).reshape(2, 3, 3) - 4.5
+    o = np.array([[1.0, 2.0, 3.0], [np.nan, np.nan, np.nan]], dtype=np.float32)
+    lines = pdb_model_lines("RX", bb, o, np.array([0.91, 0.5]))
+    assert lines[0] == "ATOM      1  N   ARG A   1      -4.500  -3.500  -2.500  1.00  0.91           N  "
+    assert lines[3][:30] == "ATOM      4  O   ARG A   1    " and lines[3][30:54] == "   1.000   2.000   3.000"
+    assert [ln[12:16] for ln in lines[:7]] == [" N  ", " CA ", " C  ", " O  ", " N  ", " CA ", " C  "]     # no O for the last residue
+    assert lines[4][17:20] == "UNK" and lines[4][22:26] == "   2" and all(len(ln) == 80 for ln in lines[:7])
+    assert lines[7].startswith("TER       8      UNK A   2") and len(lines) == 8
+    ref_pdb = Path("/root/reference/data/targets/bpti/bpti.pdb")
+    if ref_pdb.exists():            # build container only: column layout of the reference's own input file
+        first = ref_pdb.read_text().splitlines()[0]
+        assert first[:6] == "ATOM  " and first[12:16] == " N  " and first[21] == "A" and lines[0][54:60] == first[54:60]
+
+
 def test_timestep_embedder_host_mirror(golden_dir):
     from esmdiff_b200.net import TimestepEmbedder
     g = np.load(golden_dir / "timestep_embedder.npz")

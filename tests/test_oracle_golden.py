@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import esm3_emul, esm3_ref, mdlm_ref, ref_loader
+from oracle import esm3_emul, esm3_ref, mdlm_ref, ref_loader, vqvae_ref
 
 MASK = 4096
 
@@ -206,3 +206,34 @@ def test_oracle_equals_reference_live():
     torch.manual_seed(9)
     b = mdlm_ref.SamplerRef(net, emb).ddpm_sample(seq, 7)
     assert torch.equal(a, b)
+
+
+def test_decoder_oracle_geometry_and_emulation():
+    """oracle/vqvae_ref.py (esm StructureTokenDecoder restated, parity unpinned): the geometry the
+    head guarantees for any weights -- ideal N-CA / CA-C bond lengths from BB_COORDINATES, right-handed
+    orthonormal frames, |C-O| = |O_VECTOR|, NaN oxygen exactly at BOS / EOS / the last residue, pLDDT
+    in [0, 1] -- and the bf16-emulating decode with every rounding off equals the fp32 decode."""
+    dims = vqvae_ref.DecoderDimsRef(d_model=256, n_heads=4, n_layers=2)
+    dec = vqvae_ref.build_decoder(dims, seed=4)
+    g = torch.Generator().manual_seed(5)
+    tok = torch.randint(0, 4096, (2, 37), generator=g)
+    tok[:, 0], tok[:, -1] = 4098, 4097
+    out = dec.decode(tok)
+    bb, o = out["bb_pred"], out["oxygen"]
+    assert bb.shape == (2, 37, 3, 3) and o.shape == (2, 37, 3) and out["affine"].shape == (2, 37, 23)
+    n, ca, c = bb.unbind(-2)
+    assert float(((n - ca).norm(dim=-1) - 1.4592).abs().max()) < 1e-3      # |(0.5256, 1.3612, 0)|
+    assert float(((c - ca).norm(dim=-1) - 1.5251).abs().max()) < 1e-3
+    nan = torch.isnan(o).any(-1)
+    want = torch.zeros(2, 37, dtype=torch.bool)
+    want[:, 0] = want[:, -1] = want[:, -2] = True
+    assert torch.equal(nan, want)
+    assert float(((o - c)[~nan].norm(dim=-1) - 1.2311).abs().max()) < 1e-3
+    rot = vqvae_ref.graham_schmidt(torch.randn(5, 3, generator=g), torch.randn(5, 3, generator=g))
+    eye = torch.eye(3).expand(5, 3, 3)
+    assert float((rot.transpose(-1, -2) @ rot - eye).abs().max()) < 1e-5 and float((torch.linalg.det(rot) - 1).abs().max()) < 1e-5
+    assert float(out["plddt"].min()) >= 0.0 and float(out["plddt"].max()) <= 1.0
+    off = vqvae_ref.decode_emulated(dec, tok, esm3_emul.Rounding.none())
+    assert float((off["affine"] - out["affine"]).norm() / out["affine"].norm()) < 2e-5
+    on = vqvae_ref.decode_emulated(dec, tok)
+    assert 1e-4 < float((on["affine"] - out["affine"]).norm() / out["affine"].norm()) < 2e-2
