@@ -227,25 +227,37 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
             mbar_arrive(&s_empty[j & 1]);
 
             const int kv_valid = p.T - j * BKV;        // >= 1; < 64 only in the last tile
+            // Scores stay UNSCALED by the per-row factor sc (> 0, so the max commutes): the per-column
+            // factor rstd_k takes the slot of the old scale multiply and sc moves into the exp2 argument
+            // as an FMA -- folding q_ln / k_ln's 1/std in costs no arithmetic instruction here, only the
+            // broadcast reads of the table.
             float mx = -INFINITY;
+            if (fused_ln) {
+                const float4* rk4 = reinterpret_cast<const float4*>(rk_s + j * BKV);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 ra = rk4[c4], rb = rk4[c4 + 8];
+                    const float fa[4] = {ra.x, ra.y, ra.z, ra.w}, fb[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s0[4 * c4 + e] = __float_as_uint(__uint_as_float(s0[4 * c4 + e]) * fa[e]);
+                        s1[4 * c4 + e] = __float_as_uint(__uint_as_float(s1[4 * c4 + e]) * fb[e]);
+                    }
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float a = __uint_as_float(s0[c]) * sc;
-                float bq = __uint_as_float(s1[c]) * sc;
-                if (fused_ln) {
-                    a *= rk_s[j * BKV + c];
-                    bq *= rk_s[j * BKV + c + 32];
-                }
-                a = (c < kv_valid) ? a : -INFINITY;
-                bq = (c + 32 < kv_valid) ? bq : -INFINITY;
+                const float a = (c < kv_valid) ? __uint_as_float(s0[c]) : -INFINITY;
+                const float bq = (c + 32 < kv_valid) ? __uint_as_float(s1[c]) : -INFINITY;
                 s0[c] = __float_as_uint(a);
                 s1[c] = __float_as_uint(bq);
-                mx = fmaxf(mx, fmaxf(a, bq));
+                mx = fmax3(mx, a, bq);
             }
             const float m_new = fmaxf(m_run, mx);
-            const float alpha = fast_exp2(m_run - m_new);      // 0 on the first tile
+            const float alpha = fast_exp2((m_run - m_new) * sc);      // 0 on the first tile (m_run = -inf)
 #pragma unroll
             for (int d = 0; d < DH; ++d) acc[d] *= alpha;
+            const float nm = -m_new * sc;
 
             float rs = 0.f;
 #pragma unroll
@@ -254,7 +266,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
                 uint32_t w[4];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = fast_exp2(__uint_as_float(s0[c8 * 8 + i]) - m_new);
+                    e[i] = fast_exp2(fmaf(__uint_as_float(s0[c8 * 8 + i]), sc, nm));
                     rs += e[i];
                 }
 #pragma unroll
@@ -267,7 +279,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV_q,    // box [128
                 uint32_t w[4];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = fast_exp2(__uint_as_float(s1[c8 * 8 + i]) - m_new);
+                    e[i] = fast_exp2(fmaf(__uint_as_float(s1[c8 * 8 + i]), sc, nm));
                     rs += e[i];
                 }
 #pragma unroll

@@ -134,7 +134,7 @@ def bench_qk(flush):
     g = torch.Generator(device="cuda").manual_seed(7)
     e = engine()
     D, H = 1536, 24
-    for (B, T) in [(100, 258), (13, 258), (32, 514)]:
+    for (B, T) in [(100, 258), (13, 258), (32, 514), (16, 1026)]:
         M = B * T
         x = torch.randn(M, D, device=dev, generator=g)
         xs = x.view(M, D // 128, 128)
