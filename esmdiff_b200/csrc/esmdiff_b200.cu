@@ -92,6 +92,7 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    int attn_fold = 1;         // resident attention: fold a <= 4-key tail tile into the previous step (ESMDIFF_ATTN_FOLD=0: off)
     int attn_qsplit = 1;       // query-range split of the resident attention: 1 = off (default: measured no gain at 13 samples --
                                // the 16 CTAs of the second round run alone on their SMs and finish in half the time anyway),
                                // 0 = decide per launch, 2 = always; ESMDIFF_ATTN_QSPLIT
@@ -483,6 +484,8 @@ static int launch_attention(esmdiff_ctx* c, const bf16* qkv, bf16* out, int B, i
     p.ctx = out;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
     p.qk_sumsq = qk_sumsq; p.nspan = D / 128; p.ln_eps = 1e-5f;
+    // T = 64 k + e, e <= 4: the e tail keys ride on the last full step (attention_resident.cuh "Folded tail")
+    p.fold = (nkv >= 2 && T - (nkv - 1) * attn2::BKV <= attn2::FOLD_MAX && c->attn_fold) ? 1 : 0;
     CK(ensure_dynamic_smem(c->device, attn2::attention_resident_kernel, smem));
     // query-range split (attention_resident.cuh Params::q_splits): two half-length CTAs per (sample, head)
     // when that needs fewer rounds of the 2 x num_sms resident CTAs (each half reloads K/V: ~10 % extra)
@@ -928,6 +931,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_SPLIT_ROWS")) c->split_rows = atoll(e);
     if (const char* e = getenv("ESMDIFF_RESID_BN")) c->resid_bn = atoi(e);
     if (const char* e = getenv("ESMDIFF_ATTN_QSPLIT")) c->attn_qsplit = atoi(e);
+    if (const char* e = getenv("ESMDIFF_ATTN_FOLD")) c->attn_fold = atoi(e);
     c->qk_fused = c->qk_fused && c->ln_fold;
     if (const char* e = getenv("ESMDIFF_GRAPH")) c->graph_mode = atoi(e) != 0 ? 1 : 0;
     void* fn = nullptr;

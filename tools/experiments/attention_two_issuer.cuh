@@ -5,10 +5,13 @@
 //
 // One CTA = one (sample b, head h); it walks ALL query tiles of 128 rows, so K/V are read from
 // L2/HBM once per (b, h) instead of once per query tile.  Per step (query tile qt, kv tile j):
-//   MMA warp  : S = Q_qt K_j^T     UMMA 128 x ncols x 16 (x4), fp32 into one of two TMEM S buffers,
-//               issued two steps ahead of the softmax
-//               O (+)= P V_j       UMMA with A = P FROM TMEM (bf16 pairs written over the S buffer
+//   S warp    : S = Q_qt K_j^T     UMMA 128 x ncols x 16 (x4), fp32 into one of THREE TMEM S buffers,
+//               issued up to three steps ahead of the softmax (a buffer is free once the P V that
+//               read P from it has retired)
+//   P V warp  : O (+)= P V_j       UMMA with A = P FROM TMEM (bf16 pairs written over the S buffer
 //                                  by the softmax threads), B = V_j as MN-major smem operand
+//               (two issuing warps: the issue of these small MMAs plus a commit cost one warp ~1100 clk
+//               per step, more than the softmax of the step -- see the P V issuer below)
 //   4 softmax warps (thread = query row = TMEM lane): row max of the tile; the running max is only
 //               raised when the tile max exceeds it by more than 2^8 (then O is rescaled in TMEM and
 //               the row sum in its register -- rare after the first tile), p = exp2(s*scale - m),
@@ -18,10 +21,10 @@
 //   columns, not 5 x 64.  Warps whose 32 query rows are all >= T skip the softmax (the 2-row tail
 //   tile of T = 258 keeps one warp busy, not four).
 // Input  qkv : bf16 [M = B*T, 3*D]  (q | k | v, each D = H*64).  Two forms of q, k:
-//   qk_sumsq == null : q, k already LayerNormed + RoPE'd (stand-alone ew::qk_layernorm_rope_kernel)
-//   qk_sumsq != null : q' = rope(gamma_q (q - mean q)), k' likewise, NOT yet divided by their row
-//                      standard deviation, plus the per-row partial sums of (q - mean q)^2 and
-//                      (k - mean k)^2 the QKV GEMM epilogue left (gemm.cuh EPI_QKV_ROPE_LN).  The
+//   qk_rstd == null : q, k already LayerNormed + RoPE'd (stand-alone ew::qk_layernorm_rope_kernel)
+//   qk_rstd != null : q' = rope(gamma_q (q - mean q)), k' likewise, NOT yet divided by their row
+//                      standard deviation; qk_rstd holds 1/std per row (qk_rstd_kernel below, from the
+//                      partial sums of squares the QKV GEMM epilogue left, gemm.cuh EPI_QKV_ROPE_LN).  The
 //                      missing factors are per-row scalars, both applied to the fp32 scores: rstd_q[i]
 //                      goes into the softmax scale of query row i (thread = row), rstd_k[j] multiplies
 //                      score column j (one packed multiply per two scores, the factors read as
@@ -31,19 +34,34 @@
 //                      path of every CTA: +15 % kernel time; this form: see DESIGN.md.)
 // Output ctx : bf16 [M, D]
 //
-// Folded tail (Params::fold): T = 64 k + e with e <= 4 (every shape the path is quoted on: T = L + 2 with BOS and
-// EOS around L = 128, 256, 512 residues) used to cost a whole extra step per query tile for e keys -- and a step
-// is ~1.9k clk of mostly fixed latency (barrier round trips, TMEM load / store waits; clock trace in DESIGN.md)
-// whatever its width: 2 of 10 steps at T = 258.  Now the last step's S MMA is 80 columns wide (the e keys' rows
-// follow the last full K tile in shared memory), the softmax thread reads the e extra scores with one
-// tcgen05.ld.x4 and folds them into the same max / exp / row sum, writes their P as one more 16-key K-step (zeros
-// for the padding), and the P V of that step is 4 + 1 MMAs.  TMEM: S0 [0,80) S1 [80,160) O [160,224).
+// Loads (round 2, from a per-CTA clock trace, tools/attn_timeline.py): the CTAs of a wave start together,
+// ask for their 96 KB at the same moment (28 MB chip-wide = 4.4 us of HBM time with every tensor pipe
+// idle), compute together with HBM idle, and end together.  So (1) the TMA warp issues its loads BEFORE
+// the CTA-wide set-up barrier, one tile per lane in one go (a single thread needed ~140 clk per load);
+// (2) once its own tiles have landed, every CTA prefetches the tiles of the CTA that will take its place
+// (block index + resident CTAs) into L2 (cp.async.bulk.prefetch.tensor): the next wave's loads then hit
+// L2 and HBM works while the tensor pipes do; (3) the 1/std tables come from a tiny kernel run once per
+// layer instead of 24 KB of partial sums re-reduced by each of the 24 head CTAs of a sample with the
+// TMA loads held back behind them.
 #pragma once
 #include "ptx.cuh"
 
 namespace esmdiff {
 namespace attn2 {
 
+#ifndef ATTN_DBG
+#define ATTN_DBG 0      // development builds only (tools/attn_timeline.py): 32 = per-CTA clock trace, 4 = no softmax math
+#endif
+#if ATTN_DBG & 32
+constexpr int TRACE_SLOTS = 64;
+static __device__ long long g_attn_trace[4096 * TRACE_SLOTS];
+__device__ __forceinline__ void trace_ev(int slot) {
+    if (blockIdx.x < 4096 && slot < TRACE_SLOTS) g_attn_trace[blockIdx.x * TRACE_SLOTS + slot] = clock64();
+}
+#define TRACE(slot) trace_ev(slot)
+#else
+#define TRACE(slot)
+#endif
 constexpr int BQ = 128;
 constexpr int BKV = 64;
 constexpr int DH = 64;
@@ -51,12 +69,11 @@ constexpr int MAX_KV_TILES = 12;            // T <= 768
 constexpr int Q_BYTES = BQ * DH * 2;        // 16 KiB
 constexpr int KV_TILE_BYTES = BKV * DH * 2; // 8 KiB
 constexpr int BAR_BYTES = 512;
-constexpr int THREADS = 256;                // warps 0-3 softmax, 4 TMA, 5 MMA, 6-7 leftover query rows (CUDA cores)
+constexpr int THREADS = 256;                // warps 0-3 softmax, 4 TMA + S issuer, 5 P V issuer, 6-7 leftover query rows (CUDA cores)
 constexpr int MAX_LEFT = 2;                 // T mod 128 <= 2 (BOS/EOS around L = 128 k residues): no tensor tile for them
-constexpr int SBUF_COLS = 80;               // one S / P buffer: 64 columns + 16 for a folded tail
-constexpr int TMEM_COLS = 256;              // S0 [0,80) S1 [80,160) O [160,224)
-constexpr int COL_O = 160;
-constexpr int FOLD_MAX = 4;                 // T mod 64 in [1, FOLD_MAX] (and T > 64): the tail keys ride on the last full step
+constexpr int NSBUF = 3;                    // S / P buffers in TMEM
+constexpr int TMEM_COLS = 256;              // S0 [0,64) S1 [64,128) S2 [128,192) O [192,256)
+constexpr int COL_O = 192;
 constexpr float RESCALE_LOG2 = 8.0f;        // lazy rescale threshold: p <= 2^8
 
 struct Params {
@@ -72,11 +89,29 @@ struct Params {
     const __nv_bfloat16* qkv;   // [B*T, 3*H*64] (the leftover warps read their query rows directly)
     __nv_bfloat16* ctx;         // [B*T, H*64]
     float scale_log2;           // (1/sqrt(64)) * log2(e)
-    const float* qk_sumsq;      // [B*T][2 * nspan]: q spans then k spans (gemm.cuh EPI_QKV_ROPE_LN), or null
-    int nspan;                  // D / 128 partial sums per row and operand (<= 12)
-    float ln_eps;               // q_ln / k_ln epsilon
-    int fold;                   // 1: the last kv tile (<= FOLD_MAX keys) is folded into the step of the tile before it
+    const float* qk_rstd;       // q_ln / k_ln 1/std per token row: q rows at [0, M), k rows at [rstd_ld, rstd_ld + M); or null
+    long long rstd_ld;
+    int prefetch_stride;        // L2-prefetch the tiles of CTA blockIdx.x + prefetch_stride (0 = off)
 };
+
+// 1/std of every q row and k row from the QKV epilogue's per-128-column partial sums of squares
+// ([M][2 * nspan]: q spans then k spans).  One thread per (operand, row).
+__global__ void __launch_bounds__(256)
+qk_rstd_kernel(const float* __restrict__ sumsq, float* __restrict__ rstd, long long M, long long ld, int nspan, float eps) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= 2 * M) return;
+    const bool isk = idx >= M;
+    const long long row = isk ? idx - M : idx;
+    const float2* src = reinterpret_cast<const float2*>(sumsq + row * 2 * nspan + (isk ? nspan : 0));
+    float sum = 0.f;
+    for (int i = 0; i < (nspan >> 1); ++i) {
+        const float2 v = __ldg(src + i);
+        sum += v.x + v.y;
+    }
+    rstd[(isk ? ld : 0) + row] = rsqrtf(sum * (1.0f / static_cast<float>(nspan * 128)) + eps);
+}
 
 __host__ __device__ inline int kv_bytes(int nkv, int tail_cols) {
     return (nkv - 1) * KV_TILE_BYTES + tail_cols * 128;
@@ -196,13 +231,11 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     uint8_t* sV = sK + kvb;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kvb);
     uint64_t* q_full = bars;                              // [2]
-    uint64_t* q_empty = bars + 2;                         // [2]
-    uint64_t* s_full = bars + 4;                          // [2]  MMA -> softmax
-    uint64_t* p_full = bars + 6;                          // [2]  softmax warps (4 arrivals) -> MMA
-    uint64_t* pv_done = bars + 8;                         // 1    P V of step nsteps-2 retired (no S follows it)
-    uint64_t* o_free = bars + 9;                          // 1    completes once per query tile
-    uint64_t* o_full = bars + 10;                         // 1    last PV of a query tile retired
-    uint64_t* k_full = bars + 11;                         // [MAX_KV_TILES], single use
+    uint64_t* s_full = bars + 2;                          // [3]  S issuer -> softmax
+    uint64_t* p_full = bars + 5;                          // [3]  softmax warps (4 arrivals) -> P V issuer
+    uint64_t* pv_done = bars + 8;                         // [3]  P V of the step that used this buffer retired -> S issuer, rescale, epilogue
+    uint64_t* o_free = bars + 11;                         // 1    completes once per query tile
+    uint64_t* k_full = bars + 12;                         // [MAX_KV_TILES], single use
     uint64_t* v_full = k_full + MAX_KV_TILES;             // [MAX_KV_TILES], single use
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_full + MAX_KV_TILES);
     float* left_p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);   // [MAX_LEFT][nkv * 64]
@@ -219,183 +252,171 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     const int qt0 = split * p.nq / p.q_splits;                            // first query tile of this CTA
     const int nq = (split + 1) * p.nq / p.q_splits - qt0, nkv = p.nkv;   // its query tiles
     const int n_left = split == p.q_splits - 1 ? p.n_left : 0;           // trailing rows go with the last range
-    const int nst = nkv - p.fold;                                         // steps per query tile
-    const int nsteps = nq * nst;
-    const bool fused_ln = p.qk_sumsq != nullptr;
+    const bool fused_ln = p.qk_rstd != nullptr;
     uint64_t* k_ready = k_full;                           // K tiles are consumed as the TMA loads leave them
 
-    if (warp == 4 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmKV);
-        tma_prefetch_desc(&tmKVt);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&q_full[s], 1);
-            mbar_init(&q_empty[s], 1);
-            mbar_init(&s_full[s], 1);
-            mbar_init(&p_full[s], 4);              // one arrival per softmax warp
+#if ATTN_DBG & 32
+    if (threadIdx.x == 0 && blockIdx.x < 4096) {
+        g_attn_trace[blockIdx.x * TRACE_SLOTS + 0] = static_cast<long long>(global_timer_ns());
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_attn_trace[blockIdx.x * TRACE_SLOTS + 1] = smid;
+        TRACE(2);
+    }
+#endif
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmKV);
+            tma_prefetch_desc(&tmKVt);
+            for (int s = 0; s < 2; ++s) mbar_init(&q_full[s], 1);
+            for (int s = 0; s < NSBUF; ++s) {
+                mbar_init(&s_full[s], 1);
+                mbar_init(&p_full[s], 4);              // one arrival per softmax warp
+                mbar_init(&pv_done[s], 1);
+            }
+            mbar_init(o_free, 4);
+            for (int j = 0; j < nkv; ++j) {
+                mbar_init(&k_full[j], 1);
+                mbar_init(&v_full[j], 1);
+            }
+            fence_barrier_init();
         }
-        mbar_init(pv_done, 1);
-        mbar_init(o_free, 4);
-        mbar_init(o_full, 1);
-        for (int j = 0; j < nkv; ++j) {
-            mbar_init(&k_full[j], 1);
-            mbar_init(&v_full[j], 1);
+        __syncwarp();
+        // All tile loads of this CTA, one per lane, before the CTA-wide barrier: lane 0 = Q tile 0, lanes 1..nkv =
+        // K tiles, then Q tile 1 (if any), then the V tiles.  The same lanes later prefetch the same tiles of the
+        // CTA that will replace this one into L2.
+        pdl_wait();
+        const int has_q1 = nq > 1 ? 1 : 0;
+        if (lane < 2 * nkv + 1 + has_q1) {
+            const bool is_q = lane == 0 || (has_q1 && lane == nkv + 1);
+            const bool is_k = lane >= 1 && lane <= nkv;
+            const int j = is_k ? lane - 1 : lane - nkv - 1 - has_q1;       // kv tile (K or V lanes)
+            const int qt = lane == 0 ? 0 : 1;
+            const bool last = !is_q && j == nkv - 1;
+            uint64_t* bar = is_q ? &q_full[qt] : is_k ? &k_full[j] : &v_full[j];
+            uint8_t* dst = is_q ? sQ + qt * Q_BYTES : (is_k ? sK : sV) + j * KV_TILE_BYTES;
+            const CUtensorMap* tm = is_q ? &tmQ : last ? &tmKVt : &tmKV;
+            const int col = is_q ? h * DH : (is_k ? D : 2 * D) + h * DH;
+            const int rowoff = is_q ? (qt0 + qt) * BQ : j * BKV;
+            mbar_arrive_expect_tx(bar, is_q ? Q_BYTES : last ? p.tail_cols * 128 : KV_TILE_BYTES);
+            tma_load_2d(dst, tm, bar, col, row0 + rowoff);
         }
-        fence_barrier_init();
+        if (lane == 0) TRACE(3);
     }
     if (warp == 5) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
+    }
+    // 1/std of this sample's k rows and q rows (softmax + trailing-row warps): the global loads are issued here,
+    // before the set-up barrier, and land in shared memory after it
+    constexpr int RSTD_PER_THREAD = MAX_KV_TILES * BKV / 192;            // 4
+    const int rtid = warp < 4 ? threadIdx.x : threadIdx.x - 64;         // 0..191 over warps 0-3, 6-7
+    float rk[RSTD_PER_THREAD], rq[RSTD_PER_THREAD];
+    if (warp != 4) pdl_wait();
+    if (fused_ln && warp != 4 && warp != 5) {
+#pragma unroll
+        for (int u = 0; u < RSTD_PER_THREAD; ++u) {
+            const int idx = rtid + u * 192;
+            const bool in = idx < p.T;
+            rk[u] = in ? __ldg(p.qk_rstd + p.rstd_ld + row0 + idx) : 0.f;       // 0: padding keys of the last tile
+            rq[u] = in ? __ldg(p.qk_rstd + row0 + idx) : 1.f;
+        }
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_launch_dependents();
-    if (warp != 5) pdl_wait();             // every role but the MMA issuer touches global memory
-
-    if (fused_ln) {
-        // 1/std of every k row and q row of this (sample, head)'s sample from the QKV epilogue's partial
-        // sums of squares, into shared memory, by the six warps that have nothing to do until the first
-        // tiles land.  The TMA warp holds its loads back until the first batch of these small loads is in
-        // flight (named barrier 1): issued behind 82 KB of tile traffic per CTA they came back ~5k clk
-        // late, and the first S MMA needs the k factors (ncu r2c: +8k clk per CTA).
-        if (warp != 4 && warp != 5) {
-            const int tid = warp < 4 ? threadIdx.x : threadIdx.x - 64;       // 0..191
-            const int n = 2 * p.T;                                             // k rows, then q rows
-            const int half = p.nspan >> 1;
-            const float inv_n = 1.0f / static_cast<float>(p.nspan * 128);
-            bool released = false;
-#pragma unroll 1
-            for (int base = 0; base < n; base += 4 * 192) {
-                float2 raw[4][6];
+    if (fused_ln && warp != 4 && warp != 5) {
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int idx = base + b * 192 + tid;
-                    const bool isq = idx >= p.T;
-                    const int row = isq ? idx - p.T : idx;
-                    const float2* src = reinterpret_cast<const float2*>(
-                        p.qk_sumsq + static_cast<long long>(row0 + row) * 2 * p.nspan + (isq ? 0 : p.nspan));
-#pragma unroll
-                    for (int i = 0; i < 6; ++i)
-                        raw[b][i] = (idx < n && i < half) ? __ldg(src + i) : make_float2(0.f, 0.f);
-                }
-                if (!released) {
-                    named_bar_arrive(1, 224);
-                    released = true;
-                }
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int idx = base + b * 192 + tid;
-                    float sum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) sum += raw[b][i].x + raw[b][i].y;
-                    if (idx < n) (idx >= p.T ? rstd_q[idx - p.T] : rstd_k[idx]) = rsqrtf(sum * inv_n + p.ln_eps);
-                }
+        for (int u = 0; u < RSTD_PER_THREAD; ++u) {
+            const int idx = rtid + u * 192;
+            if (idx < nkv * BKV) {
+                rstd_k[idx] = rk[u];
+                rstd_q[idx] = rq[u];
             }
-            for (int idx = p.T + tid; idx < p.nkv * BKV; idx += 192) rstd_k[idx] = 0.f;      // padding keys of the last tile
-            named_bar_sync(2, 192);
-        } else if (warp == 4) {
-            named_bar_sync(1, 224);
         }
+        named_bar_sync(2, 192);
     }
 
     if (warp == 4) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            auto load_q = [&](int qt) {
-                uint64_t* bar = &q_full[qt & 1];
-                mbar_arrive_expect_tx(bar, Q_BYTES);
-                tma_load_2d(sQ + (qt & 1) * Q_BYTES, &tmQ, bar, h * DH, row0 + (qt0 + qt) * BQ);
-            };
-            auto load_kv = [&](uint8_t* dst, uint64_t* bar, int col, int j) {
-                const bool last = j == nkv - 1;
-                mbar_arrive_expect_tx(bar, last ? p.tail_cols * 128 : KV_TILE_BYTES);
-                tma_load_2d(dst + j * KV_TILE_BYTES, last ? &tmKVt : &tmKV, bar, col, row0 + j * BKV);
-            };
-            load_q(0);
-            for (int j = 0; j < nkv; ++j) load_kv(sK, &k_full[j], D + h * DH, j);
-            if (nq > 1) load_q(1);
-            for (int j = 0; j < nkv; ++j) load_kv(sV, &v_full[j], 2 * D + h * DH, j);
-            for (int qt = 2; qt < nq; ++qt) {
-                mbar_wait(&q_empty[qt & 1], ((qt >> 1) - 1) & 1);
-                load_q(qt);
+        // ===================== S = Q K^T issuer =====================
+        // The whole warp walks the schedule (warp-uniform control flow: counters and descriptors stay in uniform
+        // registers); one elected lane issues the tcgen05 instructions.  S runs up to three steps ahead of the
+        // softmax: buffer s_i % 3 is free once the P V that read P from it (step s_i - 3) has retired.
+        const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, 0);
+        const uint32_t idesc_s_tail = umma_idesc_bf16(BQ, p.tail_cols, 0);
+        const uint64_t desc_q0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
+        const uint64_t desc_k0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
+        int buf = 0, ph = 0, s_i = 0;
+        for (int s_qt = 0; s_qt < nq; ++s_qt) {
+            for (int s_j = 0; s_j < nkv; ++s_j, ++s_i) {
+                if (s_j == 0) mbar_wait(&q_full[s_qt & 1], (s_qt >> 1) & 1);
+                if (s_qt == 0) mbar_wait(&k_ready[s_j], 0);
+                if (lane == 0 && s_i < 8) TRACE(8 + s_i);               // operands in
+                if (s_i >= NSBUF) mbar_wait(&pv_done[buf], ph ^ 1);
+                if (lane == 0 && s_i < 8) TRACE(16 + s_i);              // buffer free
+                tcgen05_fence_after();
+                const uint64_t qdesc = desc_q0 + static_cast<uint64_t>((s_qt & 1) * (Q_BYTES >> 4));
+                const uint64_t kdesc = desc_k0 + static_cast<uint64_t>(s_j * (KV_TILE_BYTES >> 4));
+                const uint32_t idesc = s_j == nkv - 1 ? idesc_s_tail : idesc_s_full;
+                const uint32_t ts = tmem_base + buf * BKV;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < DH / 16; ++k)
+                        umma_bf16_ss(ts, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+                    umma_commit(&s_full[buf]);
+                }
+                __syncwarp();
+                if (lane == 0 && s_i < 8) TRACE(24 + s_i);              // S issued
+                if (++buf == NSBUF) { buf = 0; ph ^= 1; }
             }
         }
     } else if (warp == 5) {
-        // ===================== MMA issuer =====================
-        // The whole warp walks the schedule (warp-uniform control flow: counters and descriptors
-        // stay in uniform registers); one elected lane issues the tcgen05 instructions.  The
-        // first cut did this from a single thread with per-step integer divisions and took
-        // ~2.5k cycles per step -- the issuing thread, not MUFU or the tensor pipe, was the
-        // bottleneck (ncu r1c: softmax warps 33 % stalled on s_full).
+        // ===================== O += P V issuer (+ the loads of query tiles 2, 3, ...) =====================
+        // Two issuing warps because the ISSUE of these small MMAs, not their execution, bounded the step:
+        // tools/mma_bench.cu: ~45 clk per M128 N64 K16 instruction and ~190 clk per tcgen05.commit in the issuing
+        // thread against 32 clk of tensor-pipe time; one warp issuing P V_i, S_{i+2} and a commit needed ~1100 clk
+        // per step (clock trace, tools/attn_timeline.py) with the softmax warps waiting behind it.
         constexpr uint32_t idesc_pv = umma_idesc_bf16(BQ, DH, 1);       // P V : V is MN-major
-        const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, 0);
-        const uint32_t idesc_s_tail = umma_idesc_bf16(BQ, p.fold ? BKV + 16 : p.tail_cols, 0);
-        const uint64_t desc_q0 = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-        const uint64_t desc_k0 = umma_desc_sw128(smem_u32(sK), 16, 1024);
         const uint64_t desc_v0 = umma_desc_sw128(smem_u32(sV), 16, 1024);
         const uint32_t tmem_o = tmem_base + COL_O;
-        int s_i = 0, s_qt = 0, s_j = 0;                                 // next S = Q K^T to issue
-        auto issue_s = [&]() {
-            if (s_j == 0) mbar_wait(&q_full[s_qt & 1], (s_qt >> 1) & 1);
-            if (s_qt == 0) {
-                mbar_wait(&k_ready[s_j], 0);
-                if (p.fold && s_j == nst - 1) mbar_wait(&k_ready[nkv - 1], 0);      // the folded tail's rows
-            }
-            tcgen05_fence_after();
-            const uint64_t qdesc = desc_q0 + static_cast<uint64_t>((s_qt & 1) * (Q_BYTES >> 4));
-            const uint64_t kdesc = desc_k0 + static_cast<uint64_t>(s_j * (KV_TILE_BYTES >> 4));
-            const uint32_t idesc = s_j == nst - 1 ? idesc_s_tail : idesc_s_full;
-            const uint32_t ts = tmem_base + (s_i & 1) * SBUF_COLS;
-            if (elect_one()) {
-#pragma unroll
-                for (int k = 0; k < DH / 16; ++k)
-                    umma_bf16_ss(ts, qdesc + 2 * k, kdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
-                umma_commit(&s_full[s_i & 1]);
-                if (s_j == nst - 1) umma_commit(&q_empty[s_qt & 1]);
-            }
-            __syncwarp();
-            ++s_i;
-            if (++s_j == nst) { s_j = 0; ++s_qt; }
-        };
-        issue_s();
-        if (nsteps > 1) issue_s();
-        int i = 0;
+        int buf = 0, ph = 0;
         for (int qt = 0; qt < nq; ++qt) {
-            for (int j = 0; j < nst; ++j, ++i) {
-                if (qt == 0) {
-                    mbar_wait(&v_full[j], 0);
-                    if (p.fold && j == nst - 1) mbar_wait(&v_full[nkv - 1], 0);
-                }
-                mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+            for (int j = 0; j < nkv; ++j) {
+                if (qt == 0) mbar_wait(&v_full[j], 0);
+                mbar_wait(&p_full[buf], ph);
+                if (lane == 0 && qt * nkv + j < 8) TRACE(32 + qt * nkv + j);   // P ready
                 if (j == 0 && qt > 0) mbar_wait(o_free, (qt - 1) & 1);
                 tcgen05_fence_after();
                 // V tile [kv rows][64 d] is an MN-major B operand: 128-byte rows along N = d,
                 // 8-row (k) groups 1024 B apart; one UMMA K-step (16 kv rows) = 2048 B.
                 const uint64_t vdesc = desc_v0 + static_cast<uint64_t>(j * (KV_TILE_BYTES >> 4));
-                const uint32_t tp = tmem_base + (i & 1) * SBUF_COLS;    // P: bf16 pairs, 8 columns per K-step
-                const bool last = j == nst - 1;
+                const uint32_t tp = tmem_base + buf * BKV;              // P: bf16 pairs, 8 columns per K-step
+                const bool last = j == nkv - 1;
                 if (elect_one()) {
-                    if (!last || p.fold) {
+                    if (!last) {
 #pragma unroll
                         for (int k = 0; k < BKV / 16; ++k)
                             umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
-                        // folded tail: one more K-step, P at columns [64, 72) of the buffer, V rows of the tail tile
-                        if (last) umma_bf16_ts(tmem_o, tp + BKV, vdesc + (KV_TILE_BYTES >> 4), idesc_pv, 1u);
                     } else {
                         const int ksteps = p.tail_cols >> 4;
                         for (int k = 0; k < ksteps; ++k)
                             umma_bf16_ts(tmem_o, tp + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
                     }
-                    // every tcgen05.commit stalls this thread ~200 clk (tools/mma_bench.cu): the "P V of
-                    // step i retired" signal the rare rescale path needs rides on the commit of S_{i+2},
-                    // issued right behind it; only the P Vs that no S follows commit their own
-                    if (last) umma_commit(o_full);
-                    else if (s_i >= nsteps) umma_commit(pv_done);
+                    umma_commit(&pv_done[buf]);
+                    // all S of query tile qt have been consumed by the softmax (p_full of its last step): its
+                    // buffer takes query tile qt + 2
+                    if (last && qt + 2 < nq) {
+                        uint64_t* bar = &q_full[qt & 1];
+                        mbar_arrive_expect_tx(bar, Q_BYTES);
+                        tma_load_2d(sQ + (qt & 1) * Q_BYTES, &tmQ, bar, h * DH, row0 + (qt0 + qt + 2) * BQ);
+                    }
                 }
                 __syncwarp();
-                if (s_i < nsteps) issue_s();              // overwrites P_i's buffer: ordered after PV_i
+                if (lane == 0 && qt * nkv + j < 8) TRACE(40 + qt * nkv + j);   // P V issued
+                if (++buf == NSBUF) { buf = 0; ph ^= 1; }
             }
         }
     } else if (warp >= 6) {
@@ -409,6 +430,25 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                          p.ctx + static_cast<long long>(row0 + t) * D + h * DH, sK, sV, left_p + lw * nkv * BKV, p.T,
                          sc, k_ready, v_full, nkv, lane, fused_ln ? rstd_k : nullptr);
         }
+        // L2 prefetch of the tiles of the CTA that will take this one's place, once my own have landed
+        const int next = blockIdx.x + p.prefetch_stride;
+        const int has_q1 = nq > 1 ? 1 : 0;
+        if (lw == 0 && p.prefetch_stride > 0 && next < static_cast<int>(gridDim.x) && lane < 2 * nkv + 1 + has_q1) {
+            mbar_wait(&v_full[nkv - 1], 0);
+            const int nsplit = next % p.q_splits;
+            const int nh = (next / p.q_splits) % p.H;
+            const int nrow0 = (next / (p.q_splits * p.H)) * p.T;
+            const int nqt0 = nsplit * p.nq / p.q_splits;
+            const bool is_q = lane == 0 || (has_q1 && lane == nkv + 1);
+            const bool is_k = lane >= 1 && lane <= nkv;
+            const int j = is_k ? lane - 1 : lane - nkv - 1 - has_q1;
+            const int qt = lane == 0 ? 0 : 1;
+            const bool last = !is_q && j == nkv - 1;
+            const CUtensorMap* tm = is_q ? &tmQ : last ? &tmKVt : &tmKV;
+            const int col = is_q ? nh * DH : (is_k ? D : 2 * D) + nh * DH;
+            const int rowoff = is_q ? (nqt0 + qt) * BQ : j * BKV;
+            tma_prefetch_l2_2d(tm, col, nrow0 + rowoff);
+        }
     } else {
         // ===================== softmax / output warps: thread = query row =====================
         const int r = threadIdx.x;                                   // 0..127 == TMEM lane
@@ -417,8 +457,8 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
         float sc = p.scale_log2;              // per query row once q_ln's 1/std is folded in (set per query tile)
         float thresh = RESCALE_LOG2 / sc;
         // out[row] = O / l for query tile qt (after its last PV has retired), then free O
-        auto epilogue = [&](int qt, float l) {
-            mbar_wait(o_full, qt & 1);
+        auto epilogue = [&](int qt, float l, int ebuf, int eph) {
+            mbar_wait(&pv_done[ebuf], eph);                          // the last P V of query tile qt
             tcgen05_fence_after();
             if ((qt0 + qt) * BQ + warp * 32 < p.T) {
                 const float inv = 1.0f / l;
@@ -447,12 +487,23 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
 
         float m_run = 0.f;                    // running max of the raw scores (set at j == 0)
         float l_run = 0.f, l_prev = 0.f;      // running row sum (relative to m_run); previous tile's final sum
+        // Software pipeline over the steps: the TMEM loads of step i + 1's scores are issued into the score
+        // registers as soon as step i's exponentials have left them -- before step i's P stores are waited for,
+        // fenced and signalled -- so the barrier round trip (~350 clk from an arrive to the next successful wait,
+        // clock trace) and the TMEM load latency of every step hide behind the tail of the previous one.  ONE
+        // tcgen05.ld site in the loop: the registers it writes must not be touched before the wait::ld at the top
+        // of the next trip.
+        uint32_t s[64];
+        const int nsteps = nq * nkv;
+        int buf = 0, ph = 0;                  // S / P buffer of the step being computed and the parity of its use count
+        int lbuf = 0, lph = 0;                // ... of the step being loaded (one ahead)
+        int qt = 0, j = -1;                   // the step being computed; (0, -1) = none yet
 #pragma unroll 1
-        for (int qt = 0; qt < nq; ++qt) {
+        for (int step = -1; step < nsteps; ++step) {
             const bool active = (qt0 + qt) * BQ + warp * 32 < p.T;   // warp-uniform
-            for (int j = 0; j < nst; ++j) {
-                const int i = qt * nst + j;
-                const uint32_t t_s = tmem_base + lane_addr + (i & 1) * SBUF_COLS;
+            const uint32_t t_s = tmem_base + lane_addr + buf * BKV;
+            const int pbuf = buf == 0 ? NSBUF - 1 : buf - 1, pph = buf == 0 ? ph ^ 1 : ph;   // the previous step's
+            if (step >= 0) {
                 if (j == 0) {                 // new query tile: keep the finished tile's row sum for its epilogue
                     l_prev = l_run;
                     l_run = 0.f;
@@ -462,18 +513,9 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                         thresh = RESCALE_LOG2 / sc;
                     }
                 }
-                mbar_wait(&s_full[i & 1], (i >> 1) & 1);
-                tcgen05_fence_after();
-                if (active) {
-                    const bool last = j == nst - 1 && !p.fold;           // a partial tile of its own
-                    const bool ext = j == nst - 1 && p.fold;             // a full tile + the folded tail keys
+                if (active && !(ATTN_DBG & 4)) {
+                    const bool last = j == nkv - 1;
                     const int nch = (last ? p.tail_cols : BKV) >> 4;     // 16-column chunks
-                    uint32_t s[64];
-                    uint32_t sx[FOLD_MAX];                               // the folded tail's scores
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (c < nch) tmem_ld_32x32b_x16(t_s + c * 16, s + c * 16);
-                    if (ext) tmem_ld_32x32b_x4(t_s + BKV, sx);
                     tmem_ld_wait();
                     if (fused_ln) {
                         // k_ln's 1/std: one factor per score column (= key row), shared by all query rows
@@ -517,17 +559,6 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                                 m4[k] = fmax3(m4[k], __uint_as_float(s[e + 2 * k]), __uint_as_float(s[e + 2 * k + 1]));
                         mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                     }
-                    if (ext) {
-                        const int valid = p.T - (nkv - 1) * BKV;         // 1 .. FOLD_MAX tail keys
-#pragma unroll
-                        for (int e = 0; e < FOLD_MAX; ++e) {
-                            float a = __uint_as_float(sx[e]);
-                            if (fused_ln) a *= rstd_k[(nkv - 1) * BKV + e];
-                            a = e < valid ? a : -INFINITY;
-                            sx[e] = __float_as_uint(a);
-                            mx = fmaxf(mx, a);
-                        }
-                    }
                     if (j == 0) {
                         m_run = mx;
                     } else {
@@ -536,10 +567,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                             // raise the running max: rescale O and l in TMEM once PV_{i-1} has retired
                             const float m_new = need ? mx : m_run;
                             const float f = fast_exp2((m_run - m_new) * sc);
-                            // P V of step i-1 retired: implied by the commit of S_{i+1} (issued after it);
-                            // the very last step has no S_{i+1} and waits for the single pv_done commit
-                            if (i + 1 < nsteps) mbar_wait(&s_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-                            else mbar_wait(pv_done, 0);
+                            mbar_wait(&pv_done[pbuf], pph);          // P V of the previous step has retired
                             tcgen05_fence_after();
                             l_run *= f;
 #pragma unroll 1
@@ -571,31 +599,40 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
                             }
                             tmem_st_32x32b_x8(t_s + c * 8, pk);      // P over the S buffer: 2 bf16 per column
                         }
-                    if (ext) {
-                        // P of the tail keys: K-step 4 of this step's P V (16 keys = 8 columns; padding keys: p = 0)
-                        uint32_t pk[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-                        for (int e = 0; e < FOLD_MAX; e += 2) {
-                            const float p0 = fast_exp2(fmaf(__uint_as_float(sx[e]), sc, nm));
-                            const float p1 = fast_exp2(fmaf(__uint_as_float(sx[e + 1]), sc, nm));
-                            rs0 += p0;
-                            rs1 += p1;
-                            pk[e >> 1] = pack_bf16x2(p0, p1);
-                        }
-                        tmem_st_32x32b_x8(t_s + BKV, pk);
-                    }
                     l_run += rs0 + rs1;
-                    tmem_st_wait();
                 }
+            }
+            // ---- the next step's scores: wait for its S and start the TMEM loads ----
+            if (step + 1 < nsteps) {
+                int lqt = qt, lj = j + 1;
+                if (lj == nkv) { lj = 0; ++lqt; }
+                mbar_wait(&s_full[lbuf], lph);
+                if (threadIdx.x == 0 && step + 1 < 8) TRACE(48 + step + 1);   // S seen by softmax warp 0
+                tcgen05_fence_after();
+                if ((qt0 + lqt) * BQ + warp * 32 < p.T && !(ATTN_DBG & 4)) {
+                    const int nch = (lj == nkv - 1 ? p.tail_cols : BKV) >> 4;
+                    const uint32_t t_l = tmem_base + lane_addr + lbuf * BKV;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nch) tmem_ld_32x32b_x16(t_l + c * 16, s + c * 16);
+                }
+                if (++lbuf == NSBUF) { lbuf = 0; lph ^= 1; }
+            }
+            if (step >= 0) {
+                if (active && !(ATTN_DBG & 4)) tmem_st_wait();
                 // one arrival per warp: 128 per-thread arrivals are 128 serialised shared-memory atomics
                 // on the critical path of every step
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&p_full[i & 1]);
-                if (j == 0 && qt > 0) epilogue(qt - 1, l_prev);   // deferred: overlaps this tile's first MMAs
+                if (lane == 0) mbar_arrive(&p_full[buf]);
+                if (threadIdx.x == 0 && step < 8) TRACE(56 + step);   // softmax warp 0 done
+                if (j == 0 && qt > 0) epilogue(qt - 1, l_prev, pbuf, pph);   // deferred: overlaps this tile's first MMAs
+                if (++buf == NSBUF) { buf = 0; ph ^= 1; }
             }
+            if (++j == nkv && step + 1 < nsteps) { j = 0; ++qt; }
         }
-        epilogue(nq - 1, l_run);
+        epilogue(nq - 1, l_run, buf == 0 ? NSBUF - 1 : buf - 1, buf == 0 ? ph ^ 1 : ph);
+        if (threadIdx.x == 0) TRACE(4);
     }
 
     tcgen05_fence_before();
@@ -603,6 +640,7 @@ attention_resident_kernel(const __grid_constant__ CUtensorMap tmQ,      // box [
     if (warp == 5) {
         tcgen05_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
+        if (lane == 0) TRACE(5);
     }
 }
 

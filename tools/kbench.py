@@ -70,7 +70,7 @@ def bench_gemm(flush):
 
 def bench_attn(flush):
     g = torch.Generator(device="cuda").manual_seed(5)
-    engs = {"resident": engine(), "stream": engine(ESMDIFF_ATTN="stream")}
+    engs = {"resident": engine(ESMDIFF_ATTN="resident"), "stream": engine(ESMDIFF_ATTN="stream")}
     # correctness first
     for (B, T, H) in [(1, 64, 1), (2, 60, 4), (2, 130, 4), (3, 258, 24), (1, 514, 4), (2, 129, 3), (5, 1, 2), (1, 700, 2)]:
         D = H * 64
@@ -105,6 +105,61 @@ def bench_attn(flush):
         for tag, e in engs.items():
             ms = timeit(lambda: e.op_attention(qkv, B, T, H), flush=flush)
             line += f"  {tag} {ms * 1e3:7.1f} us {4 * B * H * T * T * 64 / ms / 1e9:6.1f} TF"
+        print(line, flush=True)
+    for e in engs.values():
+        e.close()
+
+
+def bench_attn_ln(flush):
+    """Resident attention, one vs two softmax threads per query row, with the q_ln / k_ln 1/std applied to
+    the scores (the product's form): parity against torch on the same inputs, then time."""
+    g = torch.Generator(device="cuda").manual_seed(8)
+    engs = {"resident": engine(ESMDIFF_ATTN="resident"), "tiles": engine(ESMDIFF_ATTN="tiles"),
+            "nofold": engine(ESMDIFF_ATTN_FOLD="0")}
+    for (B, T, H) in [(1, 64, 2), (2, 60, 4), (2, 130, 4), (3, 258, 24), (1, 514, 4), (2, 129, 3), (5, 1, 2), (1, 700, 2),
+                      (2, 33, 2), (2, 100, 2), (2, 48, 2), (1, 386, 2), (2, 17, 20), (2, 65, 4), (3, 132, 4), (2, 67, 20), (2, 68, 4),
+                      (2, 69, 4), (2, 259, 4), (1, 514, 24), (2, 194, 4)]:
+        D = H * 64
+        nspan = D // 128 if D % 256 == 0 else 0
+        qkv = (torch.randn(B * T, 3 * D, device=dev, generator=g) * 1.5).bfloat16()
+        line = f"  attention_ln B={B} T={T} H={H}:"
+        for with_ln in ((False, True) if nspan else (False,)):
+            q, k, v = [z.view(B, T, H, 64).transpose(1, 2) for z in qkv.float().chunk(3, -1)]
+            sumsq = None
+            if with_ln:
+                sumsq = (torch.rand(B * T, 2 * nspan, device=dev, generator=g) * 200 + 20).contiguous()
+                rq = torch.rsqrt(sumsq[:, :nspan].sum(-1) / D + 1e-5).view(B, 1, T, 1)
+                rk = torch.rsqrt(sumsq[:, nspan:].sum(-1) / D + 1e-5).view(B, 1, T, 1)
+                q, k = q * rq, k * rk
+            ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, D)
+            for tag, e in engs.items():
+                got = e.op_attention(qkv, B, T, H, qk_sumsq=sumsq)
+                e.synchronize()
+                err = (got.float() - ref).norm() / ref.norm()
+                line += f"  {tag}{'+ln' if with_ln else ''} {err.item():.2e}/{int(torch.isnan(got.float()).sum())}"
+        print(line, flush=True)
+    B, T, H = 2, 258, 4
+    D = H * 64
+    qkv = (torch.randn(B * T, 3 * D, device=dev, generator=g)).bfloat16()
+    qkv[:, :2 * D] *= 6.0
+    qkv[::7, D:2 * D] *= 3.0                 # a few dominant keys: exercises the lazy rescale in both halves
+    q, k, v = [z.view(B, T, H, 64).transpose(1, 2) for z in qkv.float().chunk(3, -1)]
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B * T, D)
+    for tag, e in engs.items():
+        got = e.op_attention(qkv, B, T, H)
+        e.synchronize()
+        print(f"  attention peaked logits {tag}: rel_fro={((got.float() - ref).norm() / ref.norm()).item():.2e}", flush=True)
+    for (B, T, H) in [(100, 258, 24), (100, 256, 24), (13, 258, 24), (25, 258, 24), (32, 514, 24), (64, 514, 24),
+                      (32, 766, 24), (100, 130, 24), (100, 258, 20)]:
+        D = H * 64
+        nspan = D // 128
+        qkv = torch.randn(B * T, 3 * D, device=dev, generator=g).bfloat16()
+        sumsq = (torch.rand(B * T, 2 * nspan, device=dev, generator=g) * 200 + 20).contiguous()
+        line = f"  attention B={B} T={T} H={H}:"
+        for tag, e in engs.items():
+            ms = timeit(lambda: e.op_attention(qkv, B, T, H), flush=flush)
+            ms2 = timeit(lambda: e.op_attention(qkv, B, T, H, qk_sumsq=sumsq), flush=flush)
+            line += f"  {tag} {ms * 1e3:6.1f} us, +ln {ms2 * 1e3:6.1f} us ({4 * B * H * T * T * 64 / ms2 / 1e9:5.0f} TF)"
         print(line, flush=True)
     for e in engs.values():
         e.close()
@@ -171,7 +226,7 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     which = sys.argv[1:] or ["attn", "gemm", "rows"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
-    table = dict(gemm=bench_gemm, attn=bench_attn, rows=bench_rows, qk=bench_qk)
+    table = dict(gemm=bench_gemm, attn=bench_attn, attn_ln=bench_attn_ln, rows=bench_rows, qk=bench_qk)
     for wname in which:
         print(f"=== {wname} ===", flush=True)
         table[wname](flush)
