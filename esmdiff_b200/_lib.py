@@ -84,6 +84,10 @@ _SIGS = {
                                       C.POINTER(C.c_float), C.c_uint64, C.c_int, _P, _P]),
     "esmdiff_ddpm_sample_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_float,
                                            C.c_uint64, C.c_int, _P]),
+    "esmdiff_gibbs_step": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                     C.c_uint64, C.c_uint32, _P]),
+    "esmdiff_gibbs_sample": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_float,
+                                       C.c_float, C.c_uint64, _P, _P]),
     "esmdiff_synchronize": (C.c_int, [_P, _P]),
     "esmdiff_launch_count": (C.c_int64, [_P]),
     "esmdiff_profile_enable": (C.c_int, [_P, C.c_int]),

@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "ptx.cuh"
 #include "sampler.cuh"
+#include "gibbs.cuh"
 
 using namespace esmdiff;
 typedef __nv_bfloat16 bf16;
@@ -92,6 +93,9 @@ struct esmdiff_ctx {
     int attn_variant = 0;      // 0 = resident K/V where it fits (attention_resident.cuh), 1 = always the streaming kernel
                                // (ESMDIFF_ATTN=stream), 2 = resident without the CUDA-core leftover rows (tiles)
     bool ln_fold = true;       // block pre-LayerNorms folded through the GEMMs; ESMDIFF_LN=separate -> stand-alone kernel
+    int* gibbs_cand = nullptr;         // per token row: candidate id of the current gibbs step (-1: not masked)
+    float* gibbs_ent = nullptr;        // ... and the entropy of its filtered distribution
+    int64_t gibbs_rows = 0;
     int attn_fold = 1;         // resident attention: fold a <= 4-key tail tile into the previous step (ESMDIFF_ATTN_FOLD=0: off)
     int attn_qsplit = 1;       // query-range split of the resident attention: 1 = off (default: measured no gain at 13 samples --
                                // the 16 CTAs of the second round run alone on their SMs and finish in half the time anyway),
@@ -1239,6 +1243,65 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
             CK(cudaEventRecord(c->ev_sjoin[h], c->sstream[h]));
             CK(cudaStreamWaitEvent(st, c->ev_sjoin[h], 0));
         }
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// --mode gibbs: esm's iterative structure-track sampler (gibbs.cuh)
+// ------------------------------------------------------------------------------------------------
+static int gibbs_step_impl(esmdiff_ctx* c, int64_t* x, const float* logits, const float* noise, int B, int T,
+                           float temperature, float top_p, int k, uint64_t seed, uint32_t step, uint32_t row_offset,
+                           cudaStream_t st) {
+    const int V = c->cfg.n_structure_heads;
+    const int64_t M = (int64_t)B * T;
+    if (V > sampler::THREADS * sampler::MAX_PER_THREAD) return c->fail("gibbs: vocabulary too large");
+    if (!(temperature > 0.f)) return c->fail("gibbs: temperature must be positive");
+    if ((size_t)T * sizeof(float) > 48 * 1024) return c->fail("gibbs: sequence too long for the commit kernel");
+    if (M > c->gibbs_rows) {
+        if (c->alloc(&c->gibbs_cand, M) || c->alloc(&c->gibbs_ent, M)) return 1;
+        c->gibbs_rows = M;
+    }
+    {
+        ProfScope prof(c, ESMDIFF_PROF_SAMPLER, (noise ? 8.0 : 4.0) * M * V, st);
+        gibbs::gibbs_rows_kernel<<<(unsigned)M, sampler::THREADS, 0, st>>>(
+            logits, (long long)V, noise, reinterpret_cast<const long long*>(x), c->gibbs_cand, c->gibbs_ent, V,
+            ESMDIFF_STRUCTURE_MASK_TOKEN /* ids below the first special id are valid */, ESMDIFF_STRUCTURE_MASK_TOKEN,
+            1.0f / temperature, top_p, (unsigned long long)seed, step, row_offset);
+        c->launches++;
+    }
+    gibbs::gibbs_commit_kernel<<<B, 256, (size_t)T * sizeof(float), st>>>(reinterpret_cast<long long*>(x), c->gibbs_cand,
+                                                                        c->gibbs_ent, T, k);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int esmdiff_gibbs_step(esmdiff_ctx* c, int64_t* x, const float* logits, const float* noise, int B, int T,
+                       float temperature, float top_p, int k, uint64_t seed, uint32_t step, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    return gibbs_step_impl(c, x, logits, noise, B, T, temperature, top_p, k, seed, step, 0, (cudaStream_t)stream);
+}
+
+int esmdiff_gibbs_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior, int B, int T, int steps,
+                         const int* k_per_step, float temperature, float top_p, uint64_t seed, int64_t* out,
+                         void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    if (!c->finalized) return c->fail("gibbs_sample: esmdiff_finalize_weights has not succeeded");
+    if (steps <= 0 || !k_per_step || !prior) return c->fail("gibbs_sample: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t M = (int64_t)B * T;
+    if (c->activate(0) || ensure_workspace(c, M)) return 1;
+    CK(cudaMemcpyAsync(out, prior, (size_t)M * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    // auxiliary_embeddings = None (esm's sampler knows nothing about the diffusion time): the conditioning row is zero
+    CK(cudaMemsetAsync(c->cond, 0, (size_t)c->cfg.d_model * sizeof(float), st));
+    for (int i = 0; i < steps; ++i) {
+        if (forward_step(c, seq, out, B, T, c->logits_ws, st)) return 1;
+        if (gibbs_step_impl(c, out, c->logits_ws, nullptr, B, T, temperature, top_p, k_per_step[i], seed, (uint32_t)i, 0, st))
+            return 1;
+    }
     return 0;
 }
 

@@ -236,6 +236,26 @@ class Engine:
                                                _ptr(out), _stream()))
         return out
 
+    def gibbs_step(self, x, logits, noise, temperature: float, top_p: float, k: int, seed: int = 0, step: int = 0):
+        """One entropy-ordered unmasking step in place on ``x`` (int64 (B,T) on device).  ``noise`` None ->
+        library Philox stream, else Exp(1) draws (B,T,V) fp32."""
+        B, T = x.shape
+        assert x.is_contiguous() and logits.is_contiguous() and (noise is None or noise.is_contiguous())
+        self._check(self.L.esmdiff_gibbs_step(self.h, _ptr(x), _ptr(logits), _ptr(noise), B, T, float(temperature),
+                                              float(top_p), int(k), int(seed), int(step), _stream()))
+        return x
+
+    def gibbs_sample(self, sequence_tokens, prior, k_per_step, temperature: float, top_p: float, seed: int = 0):
+        """Device-resident loop: ``len(k_per_step)`` x {forward without time conditioning, gibbs step}."""
+        B, T = prior.shape
+        seq = sequence_tokens.to(self.device, torch.int64).expand(B, T).contiguous()
+        pr = prior.to(self.device, torch.int64).contiguous()
+        out = torch.empty(B, T, dtype=torch.int64, device=self.device)
+        ks = (C.c_int * len(k_per_step))(*[int(k) for k in k_per_step])
+        self._check(self.L.esmdiff_gibbs_sample(self.h, _ptr(seq), _ptr(pr), B, T, len(k_per_step), ks,
+                                                float(temperature), float(top_p), int(seed), _ptr(out), _stream()))
+        return out
+
     def ddpm_sample_host(self, seq_host: torch.Tensor, prior_host, steps, eps=1e-5, seed=0,
                          noise_removal=True) -> torch.Tensor:
         """End to end through host buffers (H2D + loop + D2H inside the call)."""

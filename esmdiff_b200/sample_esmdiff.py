@@ -13,7 +13,10 @@ CUDA kernels (esmdiff_b200/decoder.py) when decoder weights are given:
 Without it: when the ``esm`` package is importable it is used exactly as the reference uses it
 (serial B=1 decodes); otherwise the sampled structure tokens are written next to where the PDB would
 go (``{stem}.structure_tokens.pt``) and the decode step is reported as skipped.
-``--mode gibbs`` (the esm SDK's own sampler) is not part of this path and is refused.
+``--mode gibbs`` (the reference's default: the esm SDK's entropy-ordered iterative sampler driving the same
+network, sample_esmdiff.py:66-130) runs through esmdiff_b200/gibbs.py on one GPU; it needs ``--ckpt`` (the
+pretrained ESM3 weights the reference falls back to cannot be fetched offline) and refuses ``--mask_ids``
+(coordinate-conditioned inpainting: geometric attention + VQ-VAE encoder are outside this path).
 Multi-GPU: ``torchrun --nproc-per-node N -m esmdiff_b200.sample_esmdiff ...`` shards the samples of
 every target over the ranks; rank 0 decodes and writes.
 """
@@ -142,12 +145,32 @@ def get_argparser():
     return p
 
 
+def _main_gibbs(args):
+    """sample_esmdiff.py:257-294 with sample_fn = minibatch_gibbs_by_esm(esm3_model=model.net); one GPU."""
+    from .gibbs import minibatch_gibbs_by_esm
+    model = load_state_dict_from_lightning_ckpt(args.ckpt, device="cuda")
+    data_path = Path(args.input)
+    assert data_path.is_dir(), f"Invalid directory {data_path} (Currently we only support pdb files in a folder as input)."
+    print(f">>> Sampling mode = {args.mode} ...")
+    output_dir = Path(args.output)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    decoder = None
+    if args.decoder_ckpt:
+        from .decoder import load_decoder
+        decoder = load_decoder(None if args.decoder_ckpt == "random" else args.decoder_ckpt)
+    for p in sorted(q for q in data_path.iterdir() if q.suffix == ".pdb"):
+        sequence = sequence_from_pdb(p)
+        mask_ids = [int(i) for i in args.mask_ids.split(",")] if args.mask_ids is not None else None
+        minibatch_gibbs_by_esm(sequence, model.net, output_dir, p.stem, num_samples=args.num_samples,
+                               num_steps=args.num_steps, mask_ids=mask_ids, decoder=decoder, seed=args.seed)
+
+
 def main(argv=None):
     args = get_argparser().parse_args(argv)
-    if args.mode != "ddpm":
-        raise SystemExit("esmdiff_b200 implements --mode ddpm only (gibbs is the esm SDK's sampler, "
-                         "outside this path)")
-    assert args.ckpt is not None, "--mode ddpm needs --ckpt (sample_esmdiff.py:252-258)"
+    assert args.ckpt is not None, ("--ckpt is required: the pretrained ESM3 weights the reference loads without it "
+                                   "(sample_esmdiff.py:36, :252-255) cannot be fetched offline")
+    if args.mode == "gibbs":
+        return _main_gibbs(args)
     # `torchrun --nproc-per-node N -m esmdiff_b200.sample_esmdiff ...`: one process per GPU, the
     # samples of every target sharded over the ranks (SURVEY.md 8e); plain `python -m` = one GPU
     rank, world, local = D.init_from_env()

@@ -119,6 +119,23 @@ int esmdiff_ddpm_sample_host(esmdiff_ctx* ctx, const int64_t* seq_host, const in
                              int B, int T, int steps, float eps, uint64_t seed, int noise_removal,
                              int64_t* out_host);
 
+/* --mode gibbs (reference slm/sample_esmdiff.py:66-130 -> esm.utils.generation.iterative_sampling_raw with
+ * GenerationConfig(track="structure", num_steps, temperature, top_p); esm==3.0.4, restated in oracle/gibbs_ref.py).
+ * One decoding step on device-resident tokens, after a forward WITHOUT time conditioning:
+ *   every still-masked row: top-p filter of the raw logits, special ids (>= 4096) excluded, candidate id =
+ *   argmax softmax(l / temperature) / Exp(1) (= torch.multinomial(p, 1)), entropy of the filtered distribution;
+ *   then the k masked positions of lowest entropy of every sample take their candidate
+ *   (esm.utils.generation._get_iterative_sampling_mask_for_prompt_and_step, strategy "entropy").
+ *   noise_dev : fp32 [B*T, 4101] Exp(1) draws of the caller (torch's exponential_()), or NULL = library Philox stream */
+int esmdiff_gibbs_step(esmdiff_ctx* ctx, int64_t* x_inout_dev, const float* logits_dev, const float* noise_dev,
+                       int B, int T, float temperature, float top_p, int k, uint64_t seed, uint32_t step,
+                       void* stream);
+/* The whole loop, device resident: out = prior (BOS, MASK..., EOS or a partly masked prompt); steps x {forward, step}.
+ *   k_per_step[steps] : host array, positions to unmask at each step (the cosine schedule, esmdiff_b200/gibbs.py) */
+int esmdiff_gibbs_sample(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t* prior_dev, int B, int T, int steps,
+                         const int* k_per_step, float temperature, float top_p, uint64_t seed, int64_t* out_dev,
+                         void* stream);
+
 /* Replaces the structure half of esm3_model.decode(prot) (slm/sample_esmdiff.py:56-61 -> esm
  * ESM3.decode -> StructureTokenDecoder.decode + ProteinChain.infer_oxygen), BATCHED over all samples
  * instead of the reference's serial B=1 loop (sample_esmdiff.py:225-230).  Context of model_kind 1.
