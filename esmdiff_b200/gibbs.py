@@ -5,7 +5,7 @@ loop -- forward without time conditioning, top-p / temperature sampling of every
 entropy-ordered unmasking on a cosine schedule -- runs device resident through
 ``esmdiff_gibbs_sample`` (csrc/gibbs.cuh) for ALL samples of a target in one batch, followed by the
 batched structure decode.  esm==3.0.4 is not vendored in the reference: the sampler semantics are
-restated (oracle/gibbs_ref.py, parity unpinned), the call-site contract (arguments, defaults, output
+restated (parity unpinned), the call-site contract (arguments, defaults, output
 directory name, chunk list, skip-if-exists) is the reference's.
 
 Not covered: inpainting (``--mask_ids`` in gibbs mode) -- it feeds backbone coordinates to the
