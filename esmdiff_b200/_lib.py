@@ -15,10 +15,17 @@ PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 LIB_PATH = PKG_DIR / "lib" / "libesmdiff_b200.so"
 SRC = PKG_DIR / "csrc" / "esmdiff_b200.cu"
+SRCS = [SRC, PKG_DIR / "csrc" / "encoder.cu"]          # one translation unit each, linked into one .so
 HEADER = REPO_ROOT / "include" / "esmdiff_b200.h"
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
+
+
+class EncoderCfg(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("v_heads", C.c_int32), ("n_layers", C.c_int32), ("ffn_hidden", C.c_int32),
+                ("d_out", C.c_int32), ("n_codes", C.c_int32), ("knn", C.c_int32), ("rel_bins", C.c_int32),
+                ("reserved", C.c_int32 * 8)]
 
 
 class EsmdiffError(RuntimeError):
@@ -34,7 +41,7 @@ class Cfg(C.Structure):
 
 
 def _sources():
-    return [SRC, HEADER] + sorted((PKG_DIR / "csrc").glob("*.cuh"))
+    return SRCS + [HEADER] + sorted((PKG_DIR / "csrc").glob("*.cuh"))
 
 
 def needs_build() -> bool:
@@ -50,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), str(SRC)]
+    cmd = [nvcc, *NVCC_FLAGS, "--threads", "2", "-o", str(LIB_PATH), *map(str, SRCS)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -110,6 +117,15 @@ _SIGS = {
     "esmdiff_op_gemm_qkv_rope": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P,
                                            _P, _P, C.c_int, C.c_int, _P]),
     "esmdiff_op_attention_ln": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "esmdiff_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.c_int, C.POINTER(_P)]),
+    "esmdiff_encoder_destroy": (C.c_int, [_P]),
+    "esmdiff_encoder_last_error": (C.c_char_p, [_P]),
+    "esmdiff_encoder_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int]),
+    "esmdiff_encoder_finalize": (C.c_int, [_P]),
+    "esmdiff_encode_structure": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "esmdiff_op_backbone_frames": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "esmdiff_op_geometric_attention": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                 _P, _P, _P]),
 }
 EXPORTED = tuple(_SIGS)
 _lib = None

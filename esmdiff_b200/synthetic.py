@@ -128,3 +128,39 @@ def random_decoder_state_dict(dims=None, device="cuda", seed: int = 0, full: boo
         h = "pairwise_classification_head."
         sd[h + "linear1.weight"], sd[h + "linear1.bias"] = lin(128, D), lin_b(128, D)
     return sd
+
+
+def random_encoder_state_dict(dims=None, device="cuda", seed: int = 0, full: bool = False) -> dict:
+    """Default-initialiser weights of esm's ``StructureTokenEncoder`` (ESM3_structure_encoder_v0 dims) under its
+    state-dict key names.  ``full`` adds the EMA bookkeeping buffers of the codebook that the path drops."""
+    from .encoder import EncoderDims
+    d = dims or EncoderDims()
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    D, F, H = d.d_model, d.ffn_hidden, d.v_heads
+
+    def lin(out_f, in_f):
+        return (torch.rand(out_f, in_f, device=dev, generator=g) * 2 - 1) / math.sqrt(in_f)
+
+    sd = {}
+    for l in range(d.n_layers):
+        p = f"transformer.blocks.{l}."
+        sd[p + "geom_attn.s_norm.weight"] = torch.ones(D, device=dev)
+        sd[p + "geom_attn.proj.weight"] = lin(15 * H, D)
+        sd[p + "geom_attn.out_proj.weight"] = lin(D, 3 * H)
+        sd[p + "geom_attn.distance_scale_per_head"] = torch.zeros(H, device=dev)
+        sd[p + "geom_attn.rotation_scale_per_head"] = torch.zeros(H, device=dev)
+        sd[p + "ffn.0.weight"] = torch.ones(D, device=dev)
+        sd[p + "ffn.0.bias"] = torch.zeros(D, device=dev)
+        sd[p + "ffn.1.weight"] = lin(2 * F, D)
+        sd[p + "ffn.3.weight"] = lin(D, F)
+    sd["transformer.norm.weight"] = torch.ones(D, device=dev)
+    sd["pre_vq_proj.weight"] = lin(d.d_out, D)
+    sd["pre_vq_proj.bias"] = (torch.rand(d.d_out, device=dev, generator=g) * 2 - 1) / math.sqrt(D)
+    sd["codebook.embeddings"] = torch.randn(d.n_codes, d.d_out, device=dev, generator=g)
+    sd["relative_positional_embedding.embedding.weight"] = 0.02 * torch.randn(2 * d.rel_bins + 2, D, device=dev, generator=g)
+    if full:
+        sd["codebook.cluster_size"] = torch.zeros(d.n_codes, device=dev)
+        sd["codebook.embeddings_avg"] = sd["codebook.embeddings"].clone()
+        sd["codebook.data_initialized"] = torch.zeros(1, device=dev)
+    return sd

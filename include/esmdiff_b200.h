@@ -152,6 +152,45 @@ int esmdiff_decode_structure(esmdiff_ctx* ctx, const int64_t* tokens_dev, int B,
                              float* bb_out_dev, float* o_out_dev, float* plddt_out_dev,
                              float* affine_out_dev, void* stream);
 
+/* ---- VQ-VAE structure encoder: the inpainting front end ------------------------------------------------
+ * Replaces the structure half of esm3_model.encode(ESMProtein(sequence, coordinates)) in protseq_to_data
+ * (slm/models/utils.py:136-137; consumers slm/sample_esmdiff.py:166-175, 197-209) -> esm tokenize_structure ->
+ * StructureTokenEncoder.encode (esm==3.0.4, restated in oracle/vqvae_enc_ref.py, parity unpinned).
+ * ESM3_structure_encoder_v0: d_model 1024, v_heads 128, 2 blocks (geometric attention + SwiGLU FFN, hidden 2816),
+ * d_out 128, 4096 codes, 16 nearest neighbours, 32 relative-position bins.  Computes in fp32 (the result is an
+ * index).  Weight keys: StructureTokenEncoder.state_dict() names ("transformer.blocks.0.geom_attn.proj.weight",
+ * "transformer.blocks.0.ffn.1.weight", "transformer.norm.weight", "pre_vq_proj.bias", "codebook.embeddings",
+ * "relative_positional_embedding.embedding.weight", ...); the codebook's EMA buffers are accepted and dropped. */
+typedef struct esmdiff_encoder esmdiff_encoder;
+typedef struct esmdiff_encoder_cfg {
+    int32_t d_model, v_heads, n_layers, ffn_hidden, d_out, n_codes, knn, rel_bins;
+    int32_t reserved[8];
+} esmdiff_encoder_cfg;
+int esmdiff_encoder_create(const esmdiff_encoder_cfg* cfg, int device, esmdiff_encoder** out);
+int esmdiff_encoder_destroy(esmdiff_encoder* enc);
+const char* esmdiff_encoder_last_error(const esmdiff_encoder* enc);   /* enc may be NULL: last create() error */
+int esmdiff_encoder_set_weight(esmdiff_encoder* enc, const char* key, const void* data, int on_device, int dtype,
+                               const int64_t* shape, int ndim);      /* dtype: ESMDIFF_F32 */
+int esmdiff_encoder_finalize(esmdiff_encoder* enc);
+/*   coords_dev        : fp32 [B, L, 3, 3]  N, CA, C per residue; NaN / inf = unknown (mask_ids: utils.py:121)
+ *   residue_index_dev : int64 [B, L] or NULL (= positions; tokenize_structure passes 1..L, same differences)
+ *   codes_out_dev     : int64 [B, L]  code per residue (frameless residues: the code nearest to pre_vq_proj.bias)
+ *   z_out_dev         : fp32 [B, L, d_out] pre-quantisation vectors, or NULL
+ *   edges_out_dev     : int32 [B, L, min(knn, L)] neighbour lists, or NULL */
+int esmdiff_encode_structure(esmdiff_encoder* enc, const float* coords_dev, const int64_t* residue_index_dev, int B,
+                             int L, int64_t* codes_out_dev, float* z_out_dev, int32_t* edges_out_dev, void* stream);
+/* Single kernels of that path (unit parity tests; the same kernels serve block 0 of the sampling network when
+ * coordinates are given, esmdiff_set_structure_coords):
+ *   build_affine3d_from_coordinates (net.py:441): rot [B*L, 9] row-major, trans [B*L, 3], mask uint8 [B*L];
+ *   GeometricReasoningOriginalImpl between proj and out_proj: proj_dev fp32 [G*S, 15 H] -> out fp32 [G*S, 3 H]
+ *   for G groups of S rows; frame_idx int32 [G*S] row -> frame (NULL: the row itself); work_dev [G*S, 15 H]. */
+int esmdiff_op_backbone_frames(const float* coords_dev, int B, int L, float* rot_out_dev, float* trans_out_dev,
+                               uint8_t* mask_out_dev, void* stream);
+int esmdiff_op_geometric_attention(const float* proj_dev, const float* rot_dev, const float* trans_dev,
+                                   const uint8_t* mask_dev, const int32_t* frame_idx_dev, const float* rot_scale_dev,
+                                   const float* dist_scale_dev, int G, int S, int H, int zero_frameless,
+                                   float* work_dev, float* out_dev, void* stream);
+
 /* Waits for the stream and reports asynchronous failures: CUDA errors, out-of-range token ids
  * (the reference raises IndexError in nn.Embedding), pipeline watchdog trips. */
 int esmdiff_synchronize(esmdiff_ctx* ctx, void* stream);

@@ -1,0 +1,258 @@
+"""SURVEY.md 8f row 3 -- the VQ-VAE structure ENCODER front end (reference slm/models/utils.py:99-146,
+slm/sample_esmdiff.py:166-175, 197-209, 278-284) and the geometric attention it is made of (also block 0 of the
+sampling network when coordinates are given, net.py:433-441).
+
+The arithmetic is esm==3.0.4's (not vendored, weights not available offline): oracle/vqvae_enc_ref.py and
+oracle/geom_ref.py are restatements, PARITY UNPINNED.  What the CPU tests pin is the restatement's own algebra
+(SE(3) invariance of the codes, masking rules, neighbour order); the GPU tests compare the CUDA path with it.
+The product computes this path in fp32: codes must be EQUAL except where the two nearest codes are closer than
+the fp32 noise of the distance (counted, bounded); pre-quantisation vectors within 2e-4 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geom_ref, vqvae_enc_ref as V
+
+DEV = "cuda"
+BPTI = "RPDFCLEPPYTGPCKARIIRYFYNAKAGLCQTFVYGGCRAKRNNFKSAEDCMRTCGGA"
+TINY = dict(d_model=128, v_heads=16, n_layers=2, d_out=32, n_codes=256)
+
+
+def rel_fro(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20))
+
+
+def _oracle_encoder(dims_kw, seed=0):
+    enc = V.build_encoder(V.EncoderDimsRef(**dims_kw), seed=seed)
+    with torch.no_grad():          # put the codes where the pre-quantisation vectors of a chain live (a trained codebook
+        z = enc.encode(V.synthetic_backbone(64, seed=99)[None], return_all=True)["z"][0]      # does); N(0, 1) codes
+        g = torch.Generator().manual_seed(seed)                                               # leave a handful of winners
+        e = enc.codebook.embeddings
+        e.copy_(z.mean(0) + 1.5 * z.std(0) * torch.randn(e.shape, generator=g))
+    return enc
+
+
+# ---------------------------------------------------------------------------------------------- CPU: the oracle
+def test_oracle_frames_and_black_hole():
+    bb = V.synthetic_backbone(12, seed=3)[None].repeat(2, 1, 1, 1)
+    bb[0, 4] = float("nan")
+    bb[0, 7, 1, 2] = float("inf")
+    bb[1] = float("nan")
+    rot, trans, mask = geom_ref.build_affine3d_from_coordinates(bb)
+    assert mask[0].tolist() == [True] * 4 + [False] + [True] * 2 + [False] + [True] * 4 and not mask[1].any()
+    eye = torch.eye(3)
+    assert torch.allclose(rot @ rot.transpose(-1, -2), eye.expand_as(rot), atol=1e-5)          # proper frames everywhere
+    assert torch.allclose(rot[1], eye.expand(12, 3, 3)) and float(trans[1].abs().max()) == 0.0   # no coordinates: identity
+    assert torch.equal(rot[0, 4], rot[0, 7]) and torch.equal(trans[0, 4], trans[0, 7])         # the black-hole frame
+    # a valid residue: CA is the origin, C on the negative x axis, N in the xy plane
+    local = torch.einsum("ji,aj->ai", rot[0, 0], bb[0, 0] - trans[0, 0])
+    assert local[1].abs().max() < 1e-5 and local[2, 0] < 0 and local[2, 1:].abs().max() < 1e-5 and abs(float(local[0, 2])) < 1e-5
+
+
+def test_oracle_knn_order_and_sequence_fallback():
+    bb = V.synthetic_backbone(40, seed=1)
+    mask = torch.ones(1, 40, dtype=torch.bool)
+    mask[0, 10:14] = False
+    edges = V.knn_graph(bb[None, :, 1], mask, 16)[0]
+    assert edges.shape == (40, 16) and edges[:, 0].tolist() == list(range(40))                  # self first
+    d = (bb[:, None, 1] - bb[None, :, 1]).norm(dim=-1)
+    i = 20
+    valid = [j for j in edges[i].tolist()]
+    assert all(mask[0, j] for j in valid)                                                        # 36 valid residues >= 16
+    assert valid == sorted(valid, key=lambda j: float(d[i, j]))
+    # a frameless residue: neighbours by sequence distance, lower index first on ties
+    assert edges[12, :5].tolist() == [12, 11, 13, 10, 14]
+    assert V.knn_graph(bb[None, :7, 1], mask[:, :7], 16).shape == (1, 7, 7)                      # L < knn
+
+
+def test_oracle_codes_are_se3_invariant_and_masking_is_local():
+    enc = _oracle_encoder(TINY)
+    bb = V.synthetic_backbone(48, seed=1)
+    a = enc.encode(bb[None], return_all=True)
+    assert len(set(a["codes"][0].tolist())) > 8                                                  # a discriminating test set-up
+    R = geom_ref.graham_schmidt(torch.tensor([0.3, -1.0, 0.5]), torch.tensor([1.0, 0.2, -0.4]))
+    b = enc.encode((bb @ R.T + torch.tensor([30.0, -12.0, 7.0]))[None], return_all=True)
+    assert rel_fro(b["z"], a["z"]) < 1e-4
+    assert float((a["codes"] == b["codes"]).float().mean()) > 0.95
+    # masking residues 5..9: their codes collapse to the code nearest to pre_vq_proj.bias; residues whose
+    # neighbourhoods do not touch them keep their codes
+    bb2 = bb.clone()
+    bb2[5:10] = float("inf")
+    c = enc.encode(bb2[None], return_all=True)
+    assert len(set(c["codes"][0, 5:10].tolist())) == 1
+    untouched = [i for i in range(48) if not any(5 <= j < 10 for j in a["edges"][0, i].tolist())]
+    assert len(untouched) > 5 and all(int(a["codes"][0, i]) == int(c["codes"][0, i]) for i in untouched)
+    tok = V.tokenize_structure(enc, bb)
+    assert tok.shape == (50,) and int(tok[0]) == 4098 and int(tok[-1]) == 4097 and int(tok[1:-1].max()) < 256
+
+
+def test_pdb_coordinates_reader(tmp_path):
+    from esmdiff_b200.encoder import ATOM37, coordinates_from_pdb, normalize_coordinates
+    assert len(ATOM37) == 37 and ATOM37[:5] == ("N", "CA", "C", "CB", "O")
+    bb = V.synthetic_backbone(5, seed=0)
+    lines = []
+    for i in range(5):
+        for a, name in enumerate(("N", "CA", "C")):
+            x, y, z = bb[i, a].tolist()
+            lines.append(f"ATOM  {3 * i + a + 1:5d}  {name:<3s} ALA A{i + 1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00           {name[0]:>2s}")
+    lines.insert(4, lines[3][:16] + "B" + lines[3][17:30] + "   0.000   0.000   0.000" + lines[3][54:])   # altloc B of residue 2's N
+    (tmp_path / "x.pdb").write_text("\n".join(lines) + "\nEND\n")
+    seq, c = coordinates_from_pdb(tmp_path / "x.pdb")
+    assert seq == "AAAAA" and c.shape == (5, 37, 3)
+    assert torch.allclose(c[:, :3], bb, atol=1e-3) and torch.isnan(c[:, 3:]).all()
+    n = normalize_coordinates(c)
+    assert torch.allclose((n[1:, 1] - n[:-1, 1]).norm(dim=-1), (bb[1:, 1] - bb[:-1, 1]).norm(dim=-1), atol=1e-3)
+    assert n[:, 1].mean(0).abs().max() < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_backbone_frames_kernel():
+    import ctypes as C
+    from esmdiff_b200 import _lib
+    L = _lib.lib()
+    bb = torch.stack([V.synthetic_backbone(70, seed=s) for s in range(3)])
+    bb[0, 4] = float("nan")
+    bb[0, 30:40, 2, 1] = float("inf")
+    bb[1] = float("nan")
+    bb[2] += 500.0
+    rot, trans, mask = geom_ref.build_affine3d_from_coordinates(bb)
+    c = bb.to(DEV).contiguous()
+    r = torch.empty(3 * 70, 9, device=DEV)
+    t = torch.empty(3 * 70, 3, device=DEV)
+    m = torch.empty(3 * 70, dtype=torch.uint8, device=DEV)
+    assert L.esmdiff_op_backbone_frames(c.data_ptr(), 3, 70, r.data_ptr(), t.data_ptr(), m.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(m.cpu().bool().view(3, 70), mask)
+    assert float((r.cpu().view(3, 70, 3, 3) - rot).abs().max()) < 2e-5
+    assert float((t.cpu().view(3, 70, 3) - trans).abs().max()) < 1e-3 * 1e-1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,S,H,use_idx,zero", [(37, 16, 128, True, 0), (5, 70, 256, False, 1), (3, 258, 64, False, 1),
+                                                 (9, 7, 16, True, 0)])
+def test_geometric_attention_kernel(G, S, H, use_idx, zero):
+    from esmdiff_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(G * 1000 + S)
+    ga = geom_ref.GeometricReasoningRef(64, H, mask_and_zero_frameless=bool(zero))
+    with torch.no_grad():
+        ga.distance_scale_per_head.copy_(torch.randn(H, generator=g))
+        ga.rotation_scale_per_head.copy_(torch.randn(H, generator=g))
+    nres = 90 if use_idx else G * S
+    bb = V.synthetic_backbone(nres, seed=S)[None]
+    bb[0, 3] = float("nan")
+    bb[0, 11] = float("nan")
+    rot, trans, mask = geom_ref.build_affine3d_from_coordinates(bb)
+    rot, trans, mask = rot[0], trans[0], mask[0]
+    idx = torch.randint(0, nres, (G, S), generator=g) if use_idx else torch.arange(G * S).view(G, S)
+    if use_idx:
+        idx[0] = torch.tensor([3, 11] * S)[:S]                           # a group whose keys are all frameless
+    p = torch.randn(G, S, 15 * H, generator=g)
+    with torch.no_grad():
+        want = ga.attention(p, rot[idx], trans[idx], mask[idx])
+    pd, out, work = p.to(DEV), torch.empty(G, S, 3 * H, device=DEV), torch.empty(G, S, 15 * H, device=DEV)
+    r, t, m = rot.reshape(-1, 9).contiguous().to(DEV), trans.contiguous().to(DEV), mask.to(torch.uint8).to(DEV)
+    idx_d = idx.to(torch.int32).to(DEV).contiguous() if use_idx else None
+    w_r, w_d = ga.rotation_scale_per_head.detach().to(DEV), ga.distance_scale_per_head.detach().to(DEV)
+    rc = L.esmdiff_op_geometric_attention(pd.data_ptr(), r.data_ptr(), t.data_ptr(), m.data_ptr(),
+                                          idx_d.data_ptr() if use_idx else None,
+                                          w_r.data_ptr(), w_d.data_ptr(), G, S, H, zero,
+                                          work.data_ptr(), out.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    err = float((out.cpu() - want).abs().max())
+    print(f"[geom attention G={G} S={S} H={H}] max abs err {err:.2e}, rel {rel_fro(out.cpu(), want):.2e}")
+    assert err < 2e-4 and rel_fro(out.cpu(), want) < 2e-5
+
+
+def _compare_codes(got, want, dist):
+    """ids equal except near-ties of the two best codes (margin below the fp32 noise of the distance)."""
+    bad = (got != want).nonzero().flatten().tolist()
+    excused = 0
+    for i in bad:
+        d = dist[i]
+        margin = float((d[got[i]] - d[want[i]]).abs())
+        assert margin < 2e-4 * float(d[want[i]].abs().clamp_min(1.0)), f"residue {i}: code {int(got[i])} vs {int(want[i])}, margin {margin}"
+        excused += 1
+    return excused
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,dims_kw,B,L", [("tiny", TINY, 2, 48), ("tiny_short", TINY, 1, 9),
+                                               ("esm3_encoder_v0", dict(), 1, 256), ("esm3_encoder_v0_b2", dict(), 2, 70)])
+def test_encoder_vs_oracle(name, dims_kw, B, L):
+    from esmdiff_b200.encoder import EncoderDims, StructureTokenEncoder
+    ref = _oracle_encoder(dims_kw, seed=1)
+    enc = StructureTokenEncoder(EncoderDims(**dims_kw))
+    enc.load_state_dict(ref.state_dict())
+    bb = torch.stack([V.synthetic_backbone(L, seed=10 + b) for b in range(B)])
+    if L > 20:
+        bb[0, 5:9] = float("inf")                          # inpainting-style holes (utils.py:121)
+        bb[B - 1, L - 3] = float("nan")
+    ri = torch.arange(1, L + 1)[None].repeat(B, 1)
+    ri[:, L // 2:] += 7                                    # a numbering gap
+    want = ref.encode(bb, residue_index=ri, return_all=True)
+    got = enc.encode(bb, residue_index=ri, return_aux=True)
+    torch.cuda.synchronize()
+    edges = got["edges"].cpu().long()
+    valid_rows = want["mask"]
+    assert torch.equal(edges[valid_rows][:, 0], want["edges"][valid_rows][:, 0])
+    same_edges = float((edges == want["edges"]).float().mean())
+    assert same_edges > 0.999, same_edges
+    z_err = rel_fro(got["z"].cpu(), want["z"])
+    excused = _compare_codes(got["codes"].cpu().flatten(), want["codes"].flatten(), want["dist"].flatten(0, 1))
+    n_codes = len(set(want["codes"].flatten().tolist()))
+    print(f"[encoder {name}] z rel {z_err:.2e}, codes differing at near-ties {excused}/{B * L}, distinct codes {n_codes}")
+    assert z_err < 2e-4
+    assert excused <= max(1, B * L // 100)
+    zq, codes = enc.encode(bb, residue_index=ri)
+    assert torch.equal(codes, got["codes"]) and torch.equal(zq.cpu(), ref.codebook.embeddings[codes.cpu()])
+
+
+@pytest.mark.gpu
+def test_encoder_is_se3_invariant_full_size():
+    """Size-independent property at the reference's dims: a rigid motion of the chain leaves the codes alone."""
+    from esmdiff_b200.encoder import load_encoder
+    enc = load_encoder(None, seed=3)
+    bb = V.synthetic_backbone(512, seed=5)
+    R = geom_ref.graham_schmidt(torch.tensor([0.3, -1.0, 0.5]), torch.tensor([1.0, 0.2, -0.4]))
+    a = enc.encode(bb[None], return_aux=True)
+    b = enc.encode((bb @ R.T + torch.tensor([30.0, -12.0, 7.0]))[None], return_aux=True)
+    assert rel_fro(b["z"], a["z"]) < 1e-4
+    assert float((a["codes"] == b["codes"]).float().mean()) > 0.98
+
+
+@pytest.mark.gpu
+def test_protseq_to_data_inpainting_front_end(tmp_path):
+    """utils.py:105-146 with mask_ids, from a PDB file: sequence '_' + ids 32 at the masked residues, their
+    coordinates inf, structure tokens BOS + codes + EOS equal to the oracle's tokenize_structure."""
+    from esmdiff_b200.encoder import EncoderDims, StructureTokenEncoder, pdb_to_data
+    from esmdiff_b200.sampling import build_prior
+    ref = _oracle_encoder(TINY, seed=2)
+    enc = StructureTokenEncoder(EncoderDims(**TINY))
+    enc.load_state_dict(ref.state_dict())
+    bb = V.synthetic_backbone(len(BPTI), seed=4)
+    three = {"R": "ARG", "P": "PRO", "D": "ASP", "F": "PHE", "C": "CYS", "L": "LEU", "E": "GLU", "Y": "TYR", "T": "THR",
+             "G": "GLY", "K": "LYS", "A": "ALA", "I": "ILE", "N": "ASN", "Q": "GLN", "V": "VAL", "S": "SER", "M": "MET"}
+    lines = []
+    for i, aa in enumerate(BPTI):
+        for a, name in enumerate(("N", "CA", "C")):
+            x, y, z = bb[i, a].tolist()
+            lines.append(f"ATOM  {3 * i + a + 1:5d}  {name:<3s} {three[aa]} A{i + 1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00           {name[0]:>2s}")
+    (tmp_path / "bpti.pdb").write_text("\n".join(lines) + "\nEND\n")
+    mask_ids = list(range(1, 9))
+    data = pdb_to_data(tmp_path / "bpti.pdb", enc, encode_only=True, mask_ids=mask_ids)
+    assert data["sequence"] == BPTI[0] + "_" * 8 + BPTI[9:]
+    assert data["sequence_tokens"][2:10].tolist() == [32] * 8 and int(data["sequence_tokens"][1]) != 32
+    assert torch.isinf(data["coordinates"][1:9]).all() and torch.isfinite(data["coordinates"][0, :3]).all()
+    rounded = torch.tensor([[float(f"{v:.3f}") for v in row] for row in bb.reshape(-1, 3).tolist()]).view(-1, 3, 3)
+    rounded[1:9] = float("inf")
+    want = V.tokenize_structure(ref, rounded)
+    got = data["structure_tokens"]
+    assert got.shape == want.shape == (len(BPTI) + 2,) and int(got[0]) == 4098 and int(got[-1]) == 4097
+    assert int((got != want).sum()) <= 1
+    # the prior the sampler starts from: token positions mask_ids set to MASK (the reference's off-by-one, :197-201)
+    prior = build_prior(got, 2, mask_ids=mask_ids)
+    assert prior.shape == (2, len(BPTI) + 2) and (prior[:, 1:9] == 4096).all() and int(prior[0, 9]) == int(got[9])
