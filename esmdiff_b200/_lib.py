@@ -37,7 +37,8 @@ class Cfg(C.Structure):
                 ("ffn_hidden", C.c_int32), ("n_structure_heads", C.c_int32),
                 ("seq_vocab", C.c_int32), ("struct_vocab", C.c_int32),
                 ("time_freq_dim", C.c_int32), ("time_conditioning", C.c_int32),
-                ("model_kind", C.c_int32), ("n_aux_out", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("model_kind", C.c_int32), ("n_aux_out", C.c_int32), ("v_heads", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 def _sources():
@@ -117,6 +118,7 @@ _SIGS = {
     "esmdiff_op_gemm_qkv_rope": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P, _P, _P,
                                            _P, _P, C.c_int, C.c_int, _P]),
     "esmdiff_op_attention_ln": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "esmdiff_set_structure_coords": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "esmdiff_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.c_int, C.POINTER(_P)]),
     "esmdiff_encoder_destroy": (C.c_int, [_P]),
     "esmdiff_encoder_last_error": (C.c_char_p, [_P]),

@@ -27,6 +27,12 @@
 using namespace esmdiff;
 typedef __nv_bfloat16 bf16;
 
+// geom.cuh kernels, compiled in encoder.cu (second translation unit of the library)
+int esmdiff_geom_frames(const float* coords, int B, int L, float* rot, float* trans, unsigned char* mask, cudaStream_t st);
+int esmdiff_geom_attention_bf16(const __nv_bfloat16* proj, float* work, const float* rot, const float* trans,
+                                const unsigned char* mask, const float* w_rot, const float* w_dist, __nv_bfloat16* out,
+                                int ldo, int B, int T, int H, cudaStream_t st);
+
 static std::string g_create_error;
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to (function, device) -- not to the process (a
@@ -76,6 +82,9 @@ struct LayerW {
     float *wqkv_f32 = nullptr, *w1_f32 = nullptr;
     float *cqkv = nullptr, *bqkv = nullptr, *c1 = nullptr, *b1 = nullptr;
     float* qk_gamma = nullptr;     // [2 D] q_ln.weight | k_ln.weight (QKV epilogue with q/k-LN + RoPE folded in)
+    // block 0's geometric attention (esm GeometricReasoningOriginalImpl; live only with structure coordinates)
+    float *g_snorm = nullptr, *g_wdist = nullptr, *g_wrot = nullptr;
+    bf16 *g_proj = nullptr, *g_out = nullptr;
     bool dirty = true;
 };
 
@@ -112,6 +121,14 @@ struct esmdiff_ctx {
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
     EncodeTiledFn encode = nullptr;
+    // esmdiff_set_structure_coords: backbone frames of the batch the next forwards run on (net.py:433-441);
+    // geom_on == false is the ddpm path's NaN coordinates (geometric attention contributes exactly 0)
+    bool geom_on = false;
+    int geom_B = 0, geom_T = 0;
+    int64_t geom_rows = 0;
+    float *g_rot = nullptr, *g_trans = nullptr, *g_work = nullptr;
+    unsigned char* g_mask = nullptr;
+    bf16* g_projout = nullptr;
 
     std::vector<LayerW> layers;
     float *seq_embed = nullptr, *struct_embed = nullptr, *plddt_w = nullptr, *plddt_b = nullptr;
@@ -555,6 +572,27 @@ static int ensure_workspace(esmdiff_ctx* c, int64_t M) {
 // (30 x d=1280, scale_residue=False).  In: c->x (fp32 stream) and, with the LayerNorms folded,
 // c->xn (bf16 copy) + c->stats.  Out: c->x.
 // ------------------------------------------------------------------------------------------------
+// Block 0's geometric attention with live frames (esmdiff_set_structure_coords): s_norm (weight-only LayerNorm)
+// -> proj on the tensor cores (bf16 [M, 15 v_heads]) -> rotate into the global frame + attention over the T keys
+// of every sample in fp32 on the CUDA cores (geom.cuh; 3-vectors, translations of tens of Angstrom: not bf16
+// work) -> out_proj with the residual epilogue.  c->att serves as the LayerNorm output and then as the
+// attention output (ld = 3 v_heads).
+static int run_geom_attention(esmdiff_ctx* c, const LayerW& w, int B, int T, float rs, int resid_epi, const GemmLN& make,
+                              cudaStream_t st) {
+    const int M = B * T, D = c->cfg.d_model, H = c->cfg.v_heads;
+    if (B != c->geom_B || T != c->geom_T)
+        return c->fail("forward: the batch shape differs from the one esmdiff_set_structure_coords was given");
+    if (!w.g_snorm || !w.g_proj || !w.g_out || !w.g_wdist || !w.g_wrot)
+        return c->fail("forward: structure coordinates are set but the geom_attn.* weights of block 0 were never loaded");
+    if (launch_layernorm(c, c->x, w.g_snorm, nullptr, c->att, M, D, st)) return 1;
+    if (launch_gemm(c, gemm::EPI_STORE_BF16, c->att, w.g_proj, M, 15 * H, D, c->g_projout, 15 * H, nullptr, 1.f, st)) return 1;
+    if (esmdiff_geom_attention_bf16(c->g_projout, c->g_work, c->g_rot, c->g_trans, c->g_mask, w.g_wrot, w.g_wdist, c->att,
+                                    3 * H, B, T, H, st))
+        return c->fail("forward: geometric attention launch failed");
+    c->launches += 2;
+    return launch_gemm(c, resid_epi, c->att, w.g_out, M, D, 3 * H, c->x, D, nullptr, rs, st, make);
+}
+
 static int run_blocks(esmdiff_ctx* c, int B, int T, cudaStream_t st) {
     const int M = B * T;
     const int D = c->cfg.d_model, F = c->cfg.ffn_hidden, H = c->cfg.n_heads;
@@ -584,7 +622,8 @@ static int run_blocks(esmdiff_ctx* c, int B, int T, cudaStream_t st) {
                 if (launch_attention(c, c->qkv, c->att, B, T, H, nullptr, st)) return 1;
             }
             if (launch_gemm(c, gemm::EPI_RESID_F32_LN, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st, make)) return 1;
-            // block 0's geometric attention contributes exactly 0 on this path
+            // block 0's geometric attention contributes exactly 0 without coordinates
+            if (l == 0 && c->geom_on && run_geom_attention(c, w, B, T, rs, gemm::EPI_RESID_F32_LN, make, st)) return 1;
             use.colsum = w.c1;
             use.stats_span = c->stats_span;
             if (launch_gemm(c, gemm::EPI_SWIGLU_BF16_LN, c->xn, w.w1, M, 2 * F, D, c->hbuf, F, w.b1, 1.f, st, use)) return 1;
@@ -597,7 +636,8 @@ static int run_blocks(esmdiff_ctx* c, int B, int T, cudaStream_t st) {
         if (launch_qk_norm_rope(c, c->qkv, w.qln_w, w.kln_w, M, T, D, st)) return 1;
         if (launch_attention(c, c->qkv, c->att, B, T, H, nullptr, st)) return 1;
         if (launch_gemm(c, gemm::EPI_RESID_F32, c->att, w.wo, M, D, D, c->x, D, nullptr, rs, st)) return 1;
-        // block 0's geometric attention contributes exactly 0 on this path
+        // block 0's geometric attention contributes exactly 0 without coordinates
+        if (l == 0 && c->geom_on && run_geom_attention(c, w, B, T, rs, gemm::EPI_RESID_F32, GemmLN(), st)) return 1;
         if (launch_layernorm(c, c->x, w.ln2_w, w.ln2_b, c->xn, M, D, st)) return 1;
         if (launch_gemm(c, gemm::EPI_SWIGLU_BF16, c->xn, w.w1, M, 2 * F, D, c->hbuf, F, nullptr, 1.f, st)) return 1;
         if (launch_gemm(c, gemm::EPI_RESID_F32, c->hbuf, w.w2, M, D, F, c->x, D, nullptr, rs, st)) return 1;
@@ -819,7 +859,17 @@ static bool resolve_key(esmdiff_ctx* c, const std::string& key, Slot* s) {
         if (l < 0 || l >= c->cfg.n_layers) return false;
         LayerW& w = c->layers[l];
         const std::string r = k.substr(dot + 1);
-        if (r.rfind("geom_attn.", 0) == 0) return skip();      // exact zero on this path (A6)
+        if (r.rfind("geom_attn.", 0) == 0) {
+            // exact zero without coordinates (A6); kept for esmdiff_set_structure_coords when v_heads is known
+            const int64_t H = c->cfg.v_heads;
+            if (H <= 0 || l != 0 || c->cfg.model_kind != 0) return skip();
+            if (r == "geom_attn.s_norm.weight") return f32(&w.g_snorm, {D});
+            if (r == "geom_attn.proj.weight") return b16(&w.g_proj, {15 * H, D});
+            if (r == "geom_attn.out_proj.weight") return b16(&w.g_out, {D, 3 * H});
+            if (r == "geom_attn.distance_scale_per_head") return f32(&w.g_wdist, {H});
+            if (r == "geom_attn.rotation_scale_per_head") return f32(&w.g_wrot, {H});
+            return false;
+        }
         if (r == "attn.layernorm_qkv.0.weight") { f32(&w.ln1_w, {D}); s->layer = l; return true; }
         if (r == "attn.layernorm_qkv.0.bias") { f32(&w.ln1_b, {D}); s->layer = l; return true; }
         if (r == "attn.layernorm_qkv.1.weight") {
@@ -1119,6 +1169,44 @@ int esmdiff_time_embed(esmdiff_ctx* c, float sigma, float* cond_out, void* strea
     return launch_time_embed(c, sigma, cond_out, (cudaStream_t)stream);
 }
 
+int esmdiff_set_structure_coords(esmdiff_ctx* c, const float* coords, int B, int T, void* stream) {
+    if (!c) return 1;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->drop_graphs();                                     // captured forwards do not contain the branch (or its frames)
+    if (!coords) {
+        c->geom_on = false;
+        return 0;
+    }
+    if (c->cfg.model_kind != 0 || c->cfg.v_heads <= 0 || c->cfg.v_heads > 256 || (3 * c->cfg.v_heads) % 64 != 0)
+        return c->fail("set_structure_coords: needs the sampling network created with 0 < v_heads <= 256, 3 v_heads % 64 == 0");
+    if (B <= 0 || T <= 0) return c->fail("set_structure_coords: B and T must be positive");
+    const int64_t M = (int64_t)B * T, H = c->cfg.v_heads;
+    if (M > c->geom_rows) {
+        CK(cudaStreamSynchronize(st));
+        void* olds[] = {c->g_rot, c->g_trans, c->g_work, c->g_mask, c->g_projout};
+        for (void* o : olds)
+            if (o) {
+                cudaFree(o);
+                for (auto& q : c->owned)
+                    if (q == o) q = nullptr;
+            }
+        c->g_rot = c->g_trans = c->g_work = nullptr; c->g_mask = nullptr; c->g_projout = nullptr;
+        c->geom_rows = 0;
+        c->tmaps.clear();
+        if (c->alloc(&c->g_rot, M * 9) || c->alloc(&c->g_trans, M * 3) || c->alloc(&c->g_mask, M) ||
+            c->alloc(&c->g_work, M * 15 * H) || c->alloc(&c->g_projout, M * 15 * H))
+            return 1;
+        c->geom_rows = M;
+    }
+    if (esmdiff_geom_frames(coords, B, T, c->g_rot, c->g_trans, c->g_mask, st)) return c->fail("set_structure_coords: launch failed");
+    c->launches++;
+    c->geom_on = true;
+    c->geom_B = B;
+    c->geom_T = T;
+    return 0;
+}
+
 int esmdiff_forward(esmdiff_ctx* c, const int64_t* seq, const int64_t* xt, int B, int T, const float* aux,
                     int64_t aux_row_stride, float* logits, float* emb, void* stream) {
     if (!c) return 1;
@@ -1205,7 +1293,7 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
     struct Part { int b0, nb; cudaStream_t s; };
     Part parts[2] = {{0, B, st}, {0, 0, st}};
     int nparts = 1;
-    if (B >= 2 && M <= c->split_rows && !c->prof) {
+    if (B >= 2 && M <= c->split_rows && !c->prof && !c->geom_on) {
         if (!c->sstream[0]) {
             for (int i = 0; i < 2; ++i) {
                 CK(cudaStreamCreateWithFlags(&c->sstream[i], cudaStreamNonBlocking));

@@ -73,7 +73,7 @@ class Engine:
                       1, d.plddt_bins)
         else:
             cfg = Cfg(d.d_model, d.n_heads, d.n_layers, d.ffn_hidden, d.n_structure_heads, d.seq_vocab,
-                      d.struct_vocab, d.time_freq_dim, int(d.time_conditioning))
+                      d.struct_vocab, d.time_freq_dim, int(d.time_conditioning), 0, 0, d.v_heads)
         h = C.c_void_p()
         rc = self.L.esmdiff_create(C.byref(cfg), self.device_index, C.byref(h))
         if rc != 0:
@@ -184,6 +184,19 @@ class Engine:
         self._check(self.L.esmdiff_forward(self.h, _ptr(seq), _ptr(xt), B, T, _ptr(aux), stride,
                                            _ptr(logits), _ptr(emb), _stream()))
         return logits, emb
+
+    def set_structure_coords(self, coords: torch.Tensor | None):
+        """``structure_coords`` of ``CustomizedESM3.forward`` (net.py:385, 433-441) for the NEXT forwards and sampling
+        loops: (B, T, >=3, 3) N, CA, C per token position (NaN / inf = unknown; BOS / EOS rows too), or None = the
+        ddpm path's default (no frames: block 0's geometric attention is exactly 0 and skipped)."""
+        if coords is None:
+            self._check(self.L.esmdiff_set_structure_coords(self.h, None, 0, 0, _stream()))
+            return
+        assert coords.dim() == 4 and coords.size(-1) == 3 and coords.size(-2) >= 3, "need (B, T, >=3, 3): N, CA, C"
+        B, T = coords.shape[:2]
+        c = coords[..., :3, :].to(self.device, torch.float32).contiguous()
+        self._check(self.L.esmdiff_set_structure_coords(self.h, _ptr(c), B, T, _stream()))
+        torch.cuda.current_stream().synchronize()      # `c` is a temporary: the frames are built before it goes away
 
     def forward_sigma(self, sequence_tokens, structure_tokens, sigma: float, logits_out=None):
         B, T = structure_tokens.shape

@@ -75,7 +75,7 @@ class CustomizedESM3(nn.Module):
         if labels is not None:
             raise NotImplementedError("training branch (net.py:471-481) is out of the ddpm path")
         for name, v in (("ss8_tokens", ss8_tokens), ("sasa_tokens", sasa_tokens),
-                        ("function_tokens", function_tokens), ("structure_coords", structure_coords),
+                        ("function_tokens", function_tokens),
                         ("residue_annotation_tokens", residue_annotation_tokens),
                         ("average_plddt", average_plddt), ("per_res_plddt", per_res_plddt),
                         ("sequence_id", sequence_id)):
@@ -86,8 +86,17 @@ class CustomizedESM3(nn.Module):
             raise ValueError("At least one of the inputs must be non-None")
         if sequence_tokens is None:
             sequence_tokens = torch.full_like(structure_tokens, 32)     # sequence mask id, net.py:411
-        logits, emb = self.engine.forward(sequence_tokens, structure_tokens, aux=auxiliary_embeddings,
-                                          want_embeddings=self._want_embeddings)
+        if structure_coords is not None:
+            # net.py:437-441: [..., :3, :] of an atom3 / atom14 / atom37 array -> backbone frames; block 0's
+            # geometric attention is live for this call (the ddpm path never passes coordinates: exact zero)
+            B, T = structure_tokens.shape
+            self.engine.set_structure_coords(structure_coords.expand(B, T, *structure_coords.shape[2:]))
+        try:
+            logits, emb = self.engine.forward(sequence_tokens, structure_tokens, aux=auxiliary_embeddings,
+                                              want_embeddings=self._want_embeddings)
+        finally:
+            if structure_coords is not None:
+                self.engine.set_structure_coords(None)
         return ESMOutput(sequence_logits=None, structure_logits=logits, embeddings=emb)
 
 

@@ -13,6 +13,9 @@ CUDA kernels (esmdiff_b200/decoder.py) when decoder weights are given:
 Without it: when the ``esm`` package is importable it is used exactly as the reference uses it
 (serial B=1 decodes); otherwise the sampled structure tokens are written next to where the PDB would
 go (``{stem}.structure_tokens.pt``) and the decode step is reported as skipped.
+``--mask_ids a,b,c`` (inpainting, :197-201) needs the structure tokens of the known residues: ``--encoder_ckpt PATH|random``
+runs the VQ-VAE structure ENCODER on the PDB's backbone coordinates as the reference does (esmdiff_b200/encoder.py),
+``--prior_tokens F`` takes them from a file.
 ``--mode gibbs`` (the reference's default: the esm SDK's entropy-ordered iterative sampler driving the same
 network, sample_esmdiff.py:66-130) runs through esmdiff_b200/gibbs.py on one GPU; it needs ``--ckpt`` (the
 pretrained ESM3 weights the reference falls back to cannot be fetched offline) and refuses ``--mask_ids``
@@ -72,9 +75,12 @@ def merge_pdbfiles(pdb_files, save_to: Path):
 @torch.no_grad()
 def ddpm_sample_by_esm(sequence, pl_model, output_dir: Path, sample_basename: str, num_samples=5,
                        num_steps=10, eps=1e-5, mask_ids=None, structure_tokens=None, sample_max_t=1.0,
-                       rank=0, world=1, seed=None, decoder=None):
+                       rank=0, world=1, seed=None, decoder=None, coordinates=None, esm3_model=None):
     """reference sample_esmdiff.py:137-233.  ``rank`` / ``world`` (torchrun, one process per GPU):
-    every rank samples its share of ``num_samples``; rank 0 alone decodes and writes."""
+    every rank samples its share of ``num_samples``; rank 0 alone decodes and writes.
+    ``coordinates`` (L, A, 3) + ``esm3_model`` (here: the VQ-VAE structure encoder, esmdiff_b200/encoder.py): the
+    reference's inpainting front end, ``protseq_to_data(sequence, esm3_model, encode_only=True, coordinates=,
+    mask_ids=)`` (:166-174); ``structure_tokens`` (L + 2,) given directly takes its place."""
     str_time = strftime("%Y%m%d-%H%M%S")
     output_dir = output_dir / f"step{num_steps}_eps{eps}_N{num_samples}_{str_time}"
     save_to = output_dir / f"{sample_basename}.pdb"
@@ -91,9 +97,14 @@ def ddpm_sample_by_esm(sequence, pl_model, output_dir: Path, sample_basename: st
         return None
     if rank == 0:
         output_dir.mkdir(parents=True, exist_ok=True)
+    if mask_ids is not None and structure_tokens is None:
+        assert coordinates is not None and esm3_model is not None, \
+            "inpainting needs the structure tokens of the known residues: coordinates + the VQ-VAE encoder " \
+            "(--encoder_ckpt) or --prior_tokens"
+        from .encoder import protseq_to_data
+        structure_tokens = protseq_to_data(sequence, esm3_model, encode_only=True, coordinates=coordinates,
+                                           mask_ids=mask_ids)["structure_tokens"]
     if mask_ids is not None:
-        assert structure_tokens is not None, \
-            "inpainting needs structure tokens of the known residues (VQ-VAE encoder output)"
         seq = list(sequence)
         for idx in mask_ids:
             assert 0 <= idx < len(seq), f"Invalid mask index {idx} for sequence of length {len(seq)}"
@@ -139,9 +150,13 @@ def get_argparser():
     p.add_argument("--decoder_ckpt", type=str, default=None,
                    help="(extension) esm StructureTokenDecoder state dict for the built-in batched decode, or "
                         "'random' for random-init weights of that architecture")
+    p.add_argument("--encoder_ckpt", type=str, default=None,
+                   help="(extension) esm StructureTokenEncoder state dict (data/weights/esm3_structure_encoder_v0.pth) "
+                        "for --mask_ids inpainting: the known residues' structure tokens come from the PDB's "
+                        "coordinates as in the reference; 'random' = random-init weights of that architecture")
     p.add_argument("--prior_tokens", type=str, default=None,
-                   help="(extension) .pt with 'structure_tokens' (L+2,) for --mask_ids inpainting when "
-                        "the esm VQ-VAE encoder is not installed")
+                   help="(extension) .pt with 'structure_tokens' (L+2,) for --mask_ids inpainting instead of "
+                        "--encoder_ckpt")
     return p
 
 
@@ -191,12 +206,27 @@ def main(argv=None):
     prior = None
     if args.prior_tokens:
         prior = torch.load(args.prior_tokens, weights_only=False)["structure_tokens"].to(torch.int64)
+    encoder = None
+    if args.encoder_ckpt and args.mask_ids is not None and prior is None:
+        from .encoder import load_encoder
+        encoder = load_encoder(None if args.encoder_ckpt == "random" else args.encoder_ckpt,
+                               device=local if world > 1 else None)
     for p in sorted(q for q in data_path.iterdir() if q.suffix == ".pdb"):
-        sequence = sequence_from_pdb(p)
-        mask_ids = [int(i) for i in args.mask_ids.split(",")] if args.mask_ids is not None else None
+        coordinates = None
+        if args.mask_ids is not None:
+            mask_ids = [int(i) for i in args.mask_ids.split(",")]           # 0-based index (:281)
+            if encoder is not None:
+                from .encoder import coordinates_from_pdb
+                sequence, coordinates = coordinates_from_pdb(p)             # prot.sequence, prot.coordinates (:278-283)
+            else:
+                sequence = sequence_from_pdb(p)
+        else:
+            mask_ids = None
+            sequence = sequence_from_pdb(p)
         ddpm_sample_by_esm(sequence, model, output_dir, p.stem, num_samples=args.num_samples,
                            num_steps=args.num_steps, mask_ids=mask_ids, structure_tokens=prior,
-                           rank=rank, world=world, seed=args.seed, decoder=decoder)
+                           rank=rank, world=world, seed=args.seed, decoder=decoder, coordinates=coordinates,
+                           esm3_model=encoder)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

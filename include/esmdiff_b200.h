@@ -43,7 +43,9 @@ typedef struct esmdiff_cfg {
                                  * the width of Dim6RotStructureHead.proj (23) and struct_vocab the rows of
                                  * `embed` (4101); seq_vocab, time_* are unused */
     int32_t n_aux_out;          /* model_kind 1: bins of the pLDDT head (50), 0 = head absent */
-    int32_t reserved[5];
+    int32_t v_heads;            /* 256: heads of block 0's geometric attention (net.py:341); 0 = its weights are dropped
+                                 * and esmdiff_set_structure_coords is unavailable (the ddpm path never needs them) */
+    int32_t reserved[4];
 } esmdiff_cfg;
 
 enum esmdiff_dtype { ESMDIFF_F32 = 0, ESMDIFF_BF16 = 1 };
@@ -63,7 +65,8 @@ int esmdiff_set_time_conditioning(esmdiff_ctx* ctx, int on);
  * key of the DeepSpeed ['module'] dict ("net.transformer.blocks.0.attn.out_proj.weight",
  * "sigma_embedder.mlp.0.bias", ...).  Data is copied (and converted: GEMM weights are kept in
  * bf16, FFN W1 rows are interleaved gate/up per 128).  Keys the ddpm path never reads
- * (function/residue embeddings, geom_attn.*) are accepted and dropped.  Unknown keys fail. */
+ * (function/residue embeddings; geom_attn.* when cfg.v_heads is 0) are accepted and dropped; block 0's
+ * geom_attn.* are kept for esmdiff_set_structure_coords otherwise.  Unknown keys fail. */
 int esmdiff_set_weight(esmdiff_ctx* ctx, const char* key, const void* data, int on_device,
                        int dtype, const int64_t* shape, int ndim);
 /* Strict check that every key of the path has been set; builds derived constants. */
@@ -83,6 +86,15 @@ int esmdiff_time_embed(esmdiff_ctx* ctx, float sigma, float* cond_out_dev, void*
 int esmdiff_forward(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t* xt_dev, int B, int T,
                     const float* aux_dev, int64_t aux_row_stride, float* logits_out_dev,
                     float* embeddings_out_dev, void* stream);
+/* Replaces the structure_coords argument of CustomizedESM3.forward (net.py:385, 433-441): backbone
+ * coordinates of the batch the NEXT forwards / sampling loops run on -> build_affine3d_from_coordinates, and
+ * block 0's geometric attention (esm GeometricReasoningOriginalImpl, v_heads 256, mask_and_zero_frameless=True;
+ * restated in oracle/geom_ref.py, parity unpinned) becomes live: x += out_proj(geom(s_norm(x))) / scale between the
+ * attention and the FFN of block 0.
+ *   coords_dev : fp32 [B, T, 3, 3]  N, CA, C per token position (BOS / EOS and unknown residues: NaN or inf), or
+ *                NULL = back to the default of the ddpm path (NaN everywhere: the branch is exactly 0 and skipped)
+ * Needs the geom_attn.* weights of block 0 and cfg.v_heads. */
+int esmdiff_set_structure_coords(esmdiff_ctx* ctx, const float* coords_dev, int B, int T, void* stream);
 /* Same with the time embedding computed inside from sigma (_model_wrapper, model.py:464-481). */
 int esmdiff_forward_sigma(esmdiff_ctx* ctx, const int64_t* seq_dev, const int64_t* xt_dev, int B,
                           int T, float sigma, float* logits_out_dev, void* stream);

@@ -139,7 +139,18 @@ def attention(qp, kp, v, ssq_q, ssq_k, rd: Rounding, eps: float = 1e-5):
     return out.permute(0, 2, 1, 3).reshape(B, T, D)
 
 
-def block_forward(blk, x, cos, sin, rd: Rounding, n_heads: int):
+def geom_branch(ga, x, frames, rd: Rounding):
+    """Block 0's geometric attention as run_geom_attention (esmdiff_b200.cu) evaluates it: s_norm output, proj
+    weight, proj output and the attention output are bf16 (tensor-core operands / their store epilogues); the
+    rotation into the global frame, the scores, the softmax and the weighted sum are fp32 (geom.cuh)."""
+    D = x.shape[-1]
+    ns = _r(F.layer_norm(x, (D,), ga.s_norm.weight, None, 1e-5), rd.act)
+    p = _r(_mm(ns, _r(ga.proj.weight, rd.weights), rd.f64), rd.act)
+    att = _r(ga.attention(p, *frames), rd.act)
+    return _mm(att, _r(ga.out_proj.weight, rd.weights), rd.f64)
+
+
+def block_forward(blk, x, cos, sin, rd: Rounding, n_heads: int, frames=None):
     B, T, D = x.shape
     a = blk.attn
     y = folded_linear(x, a.layernorm_qkv[0], a.layernorm_qkv[1].weight, rd, center_blocks=2)
@@ -152,7 +163,9 @@ def block_forward(blk, x, cos, sin, rd: Rounding, n_heads: int):
     att = _r(attention(qp, kp, vv, ssq_q, ssq_k, rd), rd.act)
     inv = 1.0 / torch.tensor(blk.scale, dtype=torch.float32)
     x = x + _mm(att, _r(a.out_proj.weight, rd.weights), rd.f64) * inv
-    # block 0's geometric attention is an exact zero on this path (esm3_ref.GeomAttnParamsRef)
+    # block 0's geometric attention is an exact zero without coordinates (esm3_ref.GeomAttnParamsRef)
+    if frames is not None and getattr(blk, "with_geom", False):
+        x = x + geom_branch(blk.geom_attn, x, frames, rd) * inv
     f = blk.ffn
     y = folded_linear(x, f[0], f[1].weight, rd)
     g, u = y.chunk(2, dim=-1)
@@ -162,9 +175,12 @@ def block_forward(blk, x, cos, sin, rd: Rounding, n_heads: int):
 
 @torch.no_grad()
 def forward(net: esm3_ref.CustomizedESM3Ref, structure_tokens, sequence_tokens, auxiliary_embeddings=None,
-            rd: Rounding | None = None) -> esm3_ref.NetOutput:
+            rd: Rounding | None = None, structure_coords=None) -> esm3_ref.NetOutput:
     """``CustomizedESM3Ref.forward`` with the product's rounding points."""
     B, T = structure_tokens.shape
+    frames = None
+    if structure_coords is not None:
+        frames = esm3_ref.geom_ref.build_affine3d_from_coordinates(structure_coords[..., :3, :].expand(B, T, 3, 3))
     rd = Rounding.product(T) if rd is None else rd
     dims = net.dims
     st = net.force_special_structure_ids(structure_tokens, sequence_tokens)
@@ -173,7 +189,7 @@ def forward(net: esm3_ref.CustomizedESM3Ref, structure_tokens, sequence_tokens, 
         x = x + auxiliary_embeddings
     cos, sin = esm3_ref.rotary_tables(T, dims.d_head)
     for blk in net.transformer.blocks:
-        x = block_forward(blk, x, cos, sin, rd, dims.n_heads)
+        x = block_forward(blk, x, cos, sin, rd, dims.n_heads, frames)
     emb = x
     head = net.output_heads.structure_head
     xn = _r(F.layer_norm(x, (dims.d_model,), net.transformer.norm.weight, None, 1e-5), rd.act)

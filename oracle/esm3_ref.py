@@ -32,6 +32,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import geom_ref
+
 # esm.utils.constants.esm3 values used on the path (tokenizer pins in tests/golden)
 SEQUENCE_BOS, SEQUENCE_PAD, SEQUENCE_EOS, SEQUENCE_CHAINBREAK, SEQUENCE_MASK = 0, 1, 2, 31, 32
 VQVAE_CODEBOOK_SIZE = 4096
@@ -151,25 +153,23 @@ class MultiHeadAttentionRef(nn.Module):
         return self.out_proj(ctx.transpose(1, 2).reshape(B, T, self.d))
 
 
-class GeomAttnParamsRef(nn.Module):
-    """Parameter holder for block 0's geometric attention.
+class GeomAttnParamsRef(geom_ref.GeometricReasoningRef):
+    """Block 0's geometric attention (oracle/geom_ref.py).
 
     On the ddpm path coordinates are NaN (net.py:433-441) so ``affine_mask`` is all False and,
     with ``mask_and_zero_frameless=True`` (net.py:339-345), esm zero-fills the attention
     output before a bias-free ``out_proj``: the branch contributes exactly 0.
+    With ``frames = (rot, trans, mask)`` of real coordinates it is live.
     """
 
     def __init__(self, d: int, v_heads: int):
-        super().__init__()
-        self.s_norm = nn.LayerNorm(d, bias=False)
-        self.proj = nn.Linear(d, 15 * v_heads, bias=False)
-        self.out_proj = nn.Linear(3 * v_heads, d, bias=False)
-        self.distance_scale_per_head = nn.Parameter(torch.zeros(v_heads))
-        self.rotation_scale_per_head = nn.Parameter(torch.zeros(v_heads))
+        super().__init__(d, v_heads, mask_and_zero_frameless=True)
 
-    def forward(self, x):
-        zero_ctx = torch.zeros(*x.shape[:-1], self.out_proj.in_features, dtype=x.dtype)
-        return self.out_proj(zero_ctx)      # == 0 exactly
+    def forward(self, x, frames=None):
+        if frames is None:
+            zero_ctx = torch.zeros(*x.shape[:-1], self.out_proj.in_features, dtype=x.dtype)
+            return self.out_proj(zero_ctx)      # == 0 exactly
+        return super().forward(x, *frames)
 
 
 class SwiGLURef(nn.Module):
@@ -190,10 +190,10 @@ class BlockRef(nn.Module):
                                  SwiGLURef(), nn.Linear(dims.ffn_hidden, d, bias=False))
         self.scale = dims.residue_scale
 
-    def forward(self, x):
+    def forward(self, x, frames=None):
         x = x + self.attn(x) / self.scale
         if self.with_geom:
-            x = x + self.geom_attn(x) / self.scale
+            x = x + self.geom_attn(x, frames) / self.scale
         x = x + self.ffn(x) / self.scale
         return x
 
@@ -204,9 +204,9 @@ class TransformerStackRef(nn.Module):
         self.blocks = nn.ModuleList([BlockRef(dims, i < 1) for i in range(dims.n_layers)])
         self.norm = nn.LayerNorm(dims.d_model, bias=False)
 
-    def forward(self, x):
+    def forward(self, x, frames=None):
         for blk in self.blocks:
-            x = blk(x)
+            x = blk(x, frames) if blk.with_geom else blk(x)
         return self.norm(x), x
 
 
@@ -251,15 +251,20 @@ class CustomizedESM3Ref(nn.Module):
 
     @torch.no_grad()
     def forward(self, structure_tokens, labels=None, mask=None, sequence_tokens=None, *,
-                auxiliary_embeddings=None, **unused):
+                auxiliary_embeddings=None, structure_coords=None, **unused):
         assert labels is None, "oracle covers the inference branch only (net.py:483)"
+        frames = None
+        if structure_coords is not None:                      # net.py:437-441
+            B, T = structure_tokens.shape
+            frames = geom_ref.build_affine3d_from_coordinates(
+                structure_coords[..., :3, :].expand(B, T, 3, 3))
         if sequence_tokens is None:
             sequence_tokens = torch.full_like(structure_tokens, SEQUENCE_MASK)
         st = self.force_special_structure_ids(structure_tokens, sequence_tokens)
         x = self.encoder(sequence_tokens, st)
         if auxiliary_embeddings is not None:
             x = x + auxiliary_embeddings
-        xn, emb = self.transformer(x)
+        xn, emb = self.transformer(x, frames)
         return NetOutput(structure_logits=self.output_heads.structure_head(xn), embeddings=emb)
 
 

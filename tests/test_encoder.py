@@ -256,3 +256,39 @@ def test_protseq_to_data_inpainting_front_end(tmp_path):
     # the prior the sampler starts from: token positions mask_ids set to MASK (the reference's off-by-one, :197-201)
     prior = build_prior(got, 2, mask_ids=mask_ids)
     assert prior.shape == (2, len(BPTI) + 2) and (prior[:, 1:9] == 4096).all() and int(prior[0, 9]) == int(got[9])
+
+
+@pytest.mark.gpu
+def test_network_forward_with_structure_coords_tiny():
+    """SURVEY.md 8a A6 live at tiny dims through the host mirror (``CustomizedESM3.forward(structure_coords=)``,
+    net.py:385, 433-441): block 0's geometric attention on, against the fp32 and the bf16-emulating oracle."""
+    from esmdiff_b200.net import CustomizedESM3
+    from oracle import esm3_emul, esm3_ref
+    tiny = dict(d_model=256, n_heads=4, v_heads=64, n_layers=2)
+    net, emb = esm3_ref.build_reference_model(esm3_ref.Esm3Dims(**tiny), seed=3)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        net.transformer.blocks[0].geom_attn.distance_scale_per_head.normal_(generator=g)
+        net.transformer.blocks[0].geom_attn.rotation_scale_per_head.normal_(generator=g)
+    model = CustomizedESM3(**tiny)
+    model.load_state_dict(esm3_ref.full_state_dict(net, emb))
+    B, T = 3, 70
+    seq = torch.randint(4, 24, (B, T), generator=g)
+    seq[:, 0], seq[:, -1] = 0, 2
+    xt = torch.randint(0, 4096, (B, T), generator=g)
+    xt[:, 5:30] = 4096
+    coords = torch.full((B, T, 37, 3), float("nan"))                     # an atom37 array: [..., :3, :] is used
+    coords[:, 1:-1, :3] = torch.stack([V.synthetic_backbone(T - 2, seed=20 + b) for b in range(B)])
+    coords[:, 5:30] = float("inf")
+    coords[2] = float("nan")                                             # a sample without any frame: exact zero branch
+    with torch.no_grad():
+        ref = net(xt, sequence_tokens=seq, structure_coords=coords).structure_logits
+        ref0 = net(xt, sequence_tokens=seq).structure_logits
+        emu = esm3_emul.forward(net, xt, seq, None, structure_coords=coords).structure_logits
+    got = model(xt.to(DEV), sequence_tokens=seq.to(DEV), structure_coords=coords).structure_logits.float().cpu()
+    got0 = model(xt.to(DEV), sequence_tokens=seq.to(DEV)).structure_logits.float().cpu()
+    e_ref, e_emu, effect = rel_fro(got, ref), rel_fro(got, emu), rel_fro(ref[:2], ref0[:2])
+    print(f"[structure_coords tiny] logits rel vs fp32 {e_ref:.2e}, vs emul {e_emu:.2e}, without coords {rel_fro(got0, ref0):.2e}, "
+          f"effect of the branch {effect:.3f}")
+    assert e_ref < 8.5e-3 and e_emu < 6.4e-3 and effect > 0.05
+    assert torch.equal(got[2], got0[2])                                   # frameless sample: bit-identical to no coordinates

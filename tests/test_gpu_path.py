@@ -359,6 +359,46 @@ def test_full_size_forward_vs_oracles(full_model, full_oracle, name):
     print(f"\n[T2 full size {name}] {fmt(out)}")
 
 
+def test_full_size_forward_with_structure_coords(full_model, full_oracle):
+    """SURVEY.md 8a A6 live: ``structure_coords`` given (net.py:385, 433-441) -> block 0's geometric attention
+    (v_heads = 256, T = 258 keys) contributes; residues 1..32 without coordinates (gibbs / inpainting prompt,
+    sample_esmdiff.py:92-98) and the BOS / EOS positions are frameless.  Same bounds as the other T2 cases, and
+    the branch must matter (otherwise the comparison says nothing) and must switch off again exactly."""
+    from oracle import vqvae_enc_ref
+    eng, sd = full_model
+    net, emb = full_oracle
+    seq, xt, sigma = _case("config2_B2_T258")
+    B, T = seq.shape
+    coords = torch.full((B, T, 3, 3), float("nan"))
+    coords[:, 1:-1] = vqvae_enc_ref.synthetic_backbone(T - 2, seed=7)
+    coords[:, 2:34] = float("inf")
+    g = torch.Generator().manual_seed(5)
+    ga = net.transformer.blocks[0].geom_attn                     # non-trivial per-head scales on both sides
+    wd, wr = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    with torch.no_grad():
+        ga.distance_scale_per_head.copy_(wd)
+        ga.rotation_scale_per_head.copy_(wr)
+    eng.set_weight("net.transformer.blocks.0.geom_attn.distance_scale_per_head", wd)
+    eng.set_weight("net.transformer.blocks.0.geom_attn.rotation_scale_per_head", wr)
+    eng.finalize()
+    with torch.no_grad():
+        cond = emb(torch.tensor([sigma]))[0][None, None].expand(B, T, -1)
+        ref = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond, structure_coords=coords)
+        ref0 = net(structure_tokens=xt, sequence_tokens=seq, auxiliary_embeddings=cond)
+        emu = esm3_emul.forward(net, xt, seq, cond, structure_coords=coords)
+    base, _ = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(sigma))
+    eng.set_structure_coords(coords)
+    logits, embd = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(sigma), want_embeddings=True)
+    eng.set_structure_coords(None)
+    again, _ = eng.forward(seq, xt.to(DEV), aux=eng.time_embed(sigma))
+    eng.synchronize()
+    out = parity(logits, xt, ref.structure_logits, emu.structure_logits, embd, ref.embeddings)
+    effect = rel_fro(ref.structure_logits, ref0.structure_logits)
+    print(f"\n[T2 full size structure_coords B2_T258] {fmt(out)}, effect of the branch on the logits {effect:.3f}")
+    assert effect > 10 * out["raw_rel_fp32"]
+    assert torch.equal(again, base)
+
+
 def test_config2_full_run_properties(full_model):
     """BASELINE config 2 in full (L=256, 100 samples, 25 steps, reference chunk list [63, 37])."""
     from esmdiff_b200.sampling import chunk_sizes
