@@ -18,8 +18,9 @@ runs the VQ-VAE structure ENCODER on the PDB's backbone coordinates as the refer
 ``--prior_tokens F`` takes them from a file.
 ``--mode gibbs`` (the reference's default: the esm SDK's entropy-ordered iterative sampler driving the same
 network, sample_esmdiff.py:66-130) runs through esmdiff_b200/gibbs.py on one GPU; it needs ``--ckpt`` (the
-pretrained ESM3 weights the reference falls back to cannot be fetched offline) and refuses ``--mask_ids``
-(coordinate-conditioned inpainting: geometric attention + VQ-VAE encoder are outside this path).
+pretrained ESM3 weights the reference falls back to cannot be fetched offline).  With ``--mask_ids`` (and
+``--encoder_ckpt``) the known residues' coordinates condition every forward through block 0's geometric attention
+and their VQ-VAE codes form the structure prompt.
 Multi-GPU: ``torchrun --nproc-per-node N -m esmdiff_b200.sample_esmdiff ...`` shards the samples of
 every target over the ranks; rank 0 decodes and writes.
 """
@@ -173,11 +174,22 @@ def _main_gibbs(args):
     if args.decoder_ckpt:
         from .decoder import load_decoder
         decoder = load_decoder(None if args.decoder_ckpt == "random" else args.decoder_ckpt)
+    encoder = None
+    if args.mask_ids is not None:
+        assert args.encoder_ckpt, "--mode gibbs --mask_ids conditions on the PDB's coordinates: give --encoder_ckpt PATH|random"
+        from .encoder import load_encoder
+        encoder = load_encoder(None if args.encoder_ckpt == "random" else args.encoder_ckpt)
     for p in sorted(q for q in data_path.iterdir() if q.suffix == ".pdb"):
-        sequence = sequence_from_pdb(p)
-        mask_ids = [int(i) for i in args.mask_ids.split(",")] if args.mask_ids is not None else None
+        coordinates = mask_ids = None
+        if args.mask_ids is not None:
+            from .encoder import coordinates_from_pdb
+            mask_ids = [int(i) for i in args.mask_ids.split(",")]           # 0-based index (:281)
+            sequence, coordinates = coordinates_from_pdb(p)                 # prot.sequence, prot.coordinates (:278-283)
+        else:
+            sequence = sequence_from_pdb(p)
         minibatch_gibbs_by_esm(sequence, model.net, output_dir, p.stem, num_samples=args.num_samples,
-                               num_steps=args.num_steps, mask_ids=mask_ids, decoder=decoder, seed=args.seed)
+                               num_steps=args.num_steps, coordinates=coordinates, mask_ids=mask_ids, decoder=decoder,
+                               seed=args.seed, structure_encoder=encoder)
 
 
 def main(argv=None):

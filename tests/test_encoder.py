@@ -224,6 +224,64 @@ def test_encoder_is_se3_invariant_full_size():
     assert float((a["codes"] == b["codes"]).float().mean()) > 0.98
 
 
+THREE = {"R": "ARG", "P": "PRO", "D": "ASP", "F": "PHE", "C": "CYS", "L": "LEU", "E": "GLU", "Y": "TYR", "T": "THR",
+         "G": "GLY", "K": "LYS", "A": "ALA", "I": "ILE", "N": "ASN", "Q": "GLN", "V": "VAL", "S": "SER", "M": "MET"}
+
+
+def write_backbone_pdb(path, seq, bb):
+    lines = []
+    for i, aa in enumerate(seq):
+        for a, name in enumerate(("N", "CA", "C")):
+            x, y, z = bb[i, a].tolist()
+            lines.append(f"ATOM  {3 * i + a + 1:5d}  {name:<3s} {THREE[aa]} A{i + 1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00           {name[0]:>2s}")
+    path.write_text("\n".join(lines) + "\nEND\n")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["ddpm", "gibbs"])
+def test_cli_inpainting_from_pdb_coordinates(tmp_path, capsys, mode):
+    """``--mask_ids`` end to end from a PDB with backbone coordinates (sample_esmdiff.py:278-294): the VQ-VAE encoder
+    gives the prompt's structure tokens; ddpm: prior = tokens with TOKEN positions mask_ids masked (:197-201, the
+    reference's off-by-one), every other position comes back unchanged; gibbs: the known residues keep their codes,
+    the masked ones are sampled with the known backbone frames live in block 0's geometric attention."""
+    from test_abi_and_host import write_run_dir
+    from esmdiff_b200 import sample_esmdiff
+    from esmdiff_b200.encoder import coordinates_from_pdb, load_encoder, tokenize_structure
+    from oracle import esm3_ref
+    tiny = dict(d_model=256, n_heads=4, v_heads=64, n_layers=2)
+    net, emb = esm3_ref.build_reference_model(esm3_ref.Esm3Dims(**tiny), seed=5)
+    sd = esm3_ref.full_state_dict(net, emb)
+    extra = "\n".join(f"    {k}: {v}" for k, v in tiny.items())
+    ckpt = write_run_dir(tmp_path / "run", "file", net_extra=extra, hidden=tiny["d_model"], module=sd)
+    inp = tmp_path / "targets"
+    inp.mkdir()
+    write_backbone_pdb(inp / "bpti.pdb", BPTI, V.synthetic_backbone(len(BPTI), seed=4))
+    out = tmp_path / "out"
+    mask_ids = list(range(3, 11))
+    sample_esmdiff.main(["--input", str(inp), "--ckpt", str(ckpt), "--output", str(out), "--mode", mode, "--num_steps", "6",
+                         "--num_samples", "4", "--seed", "1", "--mask_ids", ",".join(map(str, mask_ids)),
+                         "--encoder_ckpt", "random"])
+    text = capsys.readouterr().out
+    assert "Sampling token time" in text
+    saved = list(out.glob("*/bpti.structure_tokens.pt"))
+    assert len(saved) == 1
+    blob = torch.load(saved[0], weights_only=False)
+    tokens = blob["structure_tokens"]
+    assert tokens.shape == (4, len(BPTI)) and int(tokens.max()) < 4096 and int(tokens.min()) >= 0
+    assert blob["sequence"] == BPTI[:3] + "_" * 8 + BPTI[11:]
+    seq, coords = coordinates_from_pdb(inp / "bpti.pdb")
+    coords[mask_ids] = float("inf")
+    prompt = tokenize_structure(coords, load_encoder(None))[1:-1]       # the same random-init encoder (seed 0)
+    if mode == "ddpm":
+        kept = [i for i in range(len(BPTI)) if (i + 1) not in mask_ids]   # token position i + 1 <-> residue i
+    else:
+        kept = [i for i in range(len(BPTI)) if i not in mask_ids]
+        assert "Masking 8 residues and inpainting..." in text
+    assert torch.equal(tokens[:, kept], prompt[kept][None].expand(4, -1))
+    changed = [i for i in range(len(BPTI)) if i not in kept]
+    assert len(set(map(tuple, tokens[:, changed].tolist()))) > 1          # the samples differ where they were sampled
+
+
 @pytest.mark.gpu
 def test_protseq_to_data_inpainting_front_end(tmp_path):
     """utils.py:105-146 with mask_ids, from a PDB file: sequence '_' + ids 32 at the masked residues, their
@@ -234,14 +292,7 @@ def test_protseq_to_data_inpainting_front_end(tmp_path):
     enc = StructureTokenEncoder(EncoderDims(**TINY))
     enc.load_state_dict(ref.state_dict())
     bb = V.synthetic_backbone(len(BPTI), seed=4)
-    three = {"R": "ARG", "P": "PRO", "D": "ASP", "F": "PHE", "C": "CYS", "L": "LEU", "E": "GLU", "Y": "TYR", "T": "THR",
-             "G": "GLY", "K": "LYS", "A": "ALA", "I": "ILE", "N": "ASN", "Q": "GLN", "V": "VAL", "S": "SER", "M": "MET"}
-    lines = []
-    for i, aa in enumerate(BPTI):
-        for a, name in enumerate(("N", "CA", "C")):
-            x, y, z = bb[i, a].tolist()
-            lines.append(f"ATOM  {3 * i + a + 1:5d}  {name:<3s} {three[aa]} A{i + 1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}  1.00  0.00           {name[0]:>2s}")
-    (tmp_path / "bpti.pdb").write_text("\n".join(lines) + "\nEND\n")
+    write_backbone_pdb(tmp_path / "bpti.pdb", BPTI, bb)
     mask_ids = list(range(1, 9))
     data = pdb_to_data(tmp_path / "bpti.pdb", enc, encode_only=True, mask_ids=mask_ids)
     assert data["sequence"] == BPTI[0] + "_" * 8 + BPTI[9:]

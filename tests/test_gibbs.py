@@ -189,6 +189,6 @@ def test_gibbs_cli(tmp_path, capsys):
     assert len(files) == 1
     pdb = files[0].read_text()
     assert pdb.count("MODEL ") == 3 and pdb.rstrip().endswith("END")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):                                   # inpainting conditions on coordinates: needs the encoder
         sample_esmdiff.main(["--input", str(inp), "--ckpt", str(ckpt), "--output", str(out), "--mode", "gibbs",
                              "--mask_ids", "1,2,3"])
