@@ -56,6 +56,14 @@ class MaskedDiffusionLanguageModeling(nn.Module):
         self.T = T
         self.sampling_eps = sampling_eps
         self.noise_removal = noise_removal
+        self.antithetic_sampling = antithetic_sampling
+        self.change_of_variables = change_of_variables
+        self.importance_sampling = importance_sampling
+        self.condition_dropout = condition_dropout
+        self.condition_mask_rate = condition_mask_rate
+        self.structure_only = structure_only
+        self.coupled_condition_mask = coupled_condition_mask
+        self.condition_mask_index = 32                 # C.SEQUENCE_MASK_TOKEN
         self.sequence_prediction = False
         self.rng = rng
         self.vocab_size = 4101
@@ -128,6 +136,75 @@ class MaskedDiffusionLanguageModeling(nn.Module):
         if shield_special_tokens:
             logits[..., 4096:4101] += self.neg_infinity
         return logits, None
+
+    # -- training-side reuse, forward half ----------------------------------------
+    def q_xt(self, x, move_chance, condition_seq=None, non_moving_mask=None):
+        """Noisy sample x_t (reference model.py:494-513): every token moves to MASK with its sample's chance."""
+        move_indices = torch.rand(*x.shape, device=x.device) < move_chance
+        if non_moving_mask is not None:
+            move_indices = move_indices & (~non_moving_mask)
+        xt = torch.where(move_indices, self.mask_index, x)
+        if self.coupled_condition_mask and condition_seq is not None:
+            condition_seq = torch.where(move_indices, self.condition_mask_index, condition_seq)
+        return xt, condition_seq
+
+    def _sample_t(self, n, device):
+        """reference model.py:518-526 (antithetic: one stratum per sample)."""
+        _eps_t = torch.rand(n, device=device)
+        if self.antithetic_sampling:
+            offset = torch.arange(n, device=device) / n
+            _eps_t = (_eps_t / n + offset) % 1
+        t = (1 - self.sampling_eps) * _eps_t + self.sampling_eps
+        if self.importance_sampling:
+            return self.noise.importance_sampling_transformation(t)
+        return t
+
+    @torch.no_grad()
+    def model_step(self, batch, training=False):
+        """The diffusion NELBO of one batch (reference model.py:386-462) with the forward on the CUDA path:
+        ``batch`` = {"structure_tokens", "sequence_tokens", "mask"[, "non_moving_mask"]} int64 / bool (B, L).
+        Forward half only -- what ``validation_step`` / ``test_step`` need (model.py:157-196 call it and log the
+        loss); there is no backward on this path, so ``training=True`` only switches the reference's condition
+        dropout / masking on.  Random draws (t, condition mask, q_xt) are made on ``batch``'s device with torch's
+        generator in the reference's order, so a seeded CPU batch sees the reference's own noise."""
+        from random import random
+        labels = batch["structure_tokens"].detach().clone()
+        x0 = batch["structure_tokens"].detach().clone()
+        condition_seq = batch["sequence_tokens"]
+        if self.condition_dropout > 0 and training:
+            if random() < self.condition_dropout:
+                condition_seq = None
+        if self.condition_mask_rate > 0 and condition_seq is not None and training:
+            mask = (torch.rand_like(condition_seq, dtype=torch.float) < self.condition_mask_rate) & (condition_seq != 1)
+            condition_seq = torch.where(mask, self.condition_mask_index, condition_seq)
+        loss_mask = batch["mask"] * (labels != 4099)              # C.STRUCTURE_PAD_TOKEN
+        t = self._sample_t(x0.shape[0], x0.device)
+        if self.T > 0:
+            t = (t * self.T).to(torch.int) / self.T
+            t += (1 / self.T)
+        if self.change_of_variables:
+            net_conditioning = t[:, None]
+            f_T = torch.log1p(- torch.exp(- self.noise.sigma_max))
+            f_0 = torch.log1p(- torch.exp(- self.noise.sigma_min))
+            move_chance = torch.exp(f_0 + t * (f_T - f_0))[:, None]
+        else:
+            sigma, dsigma = self.noise(t)
+            net_conditioning = sigma[:, None]
+            move_chance = 1 - torch.exp(-sigma[:, None])
+        if self.structure_only:
+            condition_seq = None
+        xt, condition_seq = self.q_xt(x0, move_chance, condition_seq=condition_seq,
+                                      non_moving_mask=batch.get("non_moving_mask", None))
+        logits, _ = self._model_wrapper(xt, None if condition_seq is None else condition_seq.to(self.device),
+                                        net_conditioning)
+        log_p_theta = torch.gather(logits, -1, x0.to(self.device)[:, :, None]).squeeze(-1)
+        if self.change_of_variables or self.importance_sampling:
+            loss = log_p_theta * torch.log1p(- torch.exp(- self.noise.sigma_min))
+        else:
+            loss = - log_p_theta * (dsigma / torch.expm1(sigma)).to(self.device)[:, None]
+        loss_mask = loss_mask.to(self.device)
+        loss = (loss * loss_mask).sum() / loss_mask.sum()
+        return loss, {"nelbo": loss.detach().clone(), "xt": xt, "t": t}
 
     def _schedule(self, num_steps, eps, sample_max_t, device):
         """sigma_t, move_chance_t, move_chance_s for every step and sigma at the last grid point,

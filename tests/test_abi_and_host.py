@@ -332,3 +332,27 @@ def test_gloo_world_size_2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_model_step_noise_draws_are_the_reference_ops(golden_dir):
+    """SURVEY.md 8f row 4, host half: ``_sample_t`` (antithetic strata), the discrete-T rounding and ``q_xt`` of the
+    mirror replay the reference's own draws (tests/golden/model_step.npz, made by oracle/make_golden_model_step.py
+    from the verbatim reference, model.py:386-426, 494-526) under the same torch seed."""
+    from esmdiff_b200 import noise_utils
+    from esmdiff_b200.model import MaskedDiffusionLanguageModeling
+    g = np.load(golden_dir / "model_step.npz")
+    m = MaskedDiffusionLanguageModeling(net=None, noise_schedule=noise_utils.LogLinearNoise(), time_conditioning=True,
+                                        condition_mask_rate=0.0)
+    x0, seq = torch.from_numpy(g["structure_tokens"]), torch.from_numpy(g["sequence_tokens"])
+    for name, T in (("plain", 0), ("discrete_T", 50)):
+        torch.manual_seed(11)
+        t = m._sample_t(x0.shape[0], x0.device)
+        if T > 0:
+            t = (t * T).to(torch.int) / T
+            t += 1 / T
+        sigma, _ = m.noise(t)
+        xt, cs = m.q_xt(x0.clone(), 1 - torch.exp(-sigma[:, None]), condition_seq=seq)
+        assert np.array_equal(t.numpy(), g[f"{name}_t"]) and np.array_equal(xt.numpy(), g[f"{name}_xt"])
+        assert cs is seq                                          # coupled_condition_mask off: the sequence is untouched
+    strata = np.floor(g["plain_t"] * 4 - 1e-3 * 4 * 0)            # antithetic sampling: one draw per quarter of [eps, 1)
+    assert sorted(np.floor((g["plain_t"] - 1e-3) / (1 - 1e-3) * 4).astype(int).tolist()) == [0, 1, 2, 3]

@@ -214,6 +214,35 @@ def test_host_mirror_model_loop_matches_stepwise(tiny_pair):
     assert float((host.to(DEV) == b1).float().mean()) > 0.98
 
 
+def test_model_step_nelbo_matches_reference_golden(tiny_pair, golden_dir):
+    """SURVEY.md 8f row 4, forward half: the diffusion NELBO of one batch (``model_step``, reference model.py:386-462
+    -- what validation_step / test_step log) with the forward on the CUDA path, against the value the reference's OWN
+    model_step returned around the fp32 oracle network (tests/golden/model_step.npz).  The draws (t, x_t) are replayed
+    bit for bit from torch's CPU generator; the loss is a masked mean of log-probs: 2e-4 relative."""
+    from esmdiff_b200 import noise_utils
+    from esmdiff_b200.model import MaskedDiffusionLanguageModeling
+    from esmdiff_b200.net import TimestepEmbedder
+    net, emb, eng = tiny_pair
+    g = np.load(golden_dir / "model_step.npz")
+
+    class _Net:                                     # the fixture's engine behind the mirror's network surface
+        engine, device = eng, eng.device
+
+    te = TimestepEmbedder(256)
+    te.load_state_dict(emb.state_dict())
+    m = MaskedDiffusionLanguageModeling(net=_Net(), noise_schedule=noise_utils.LogLinearNoise(), sigma_embedder=te.to(DEV),
+                                        time_conditioning=True, condition_mask_rate=0.0)
+    batch = {k: torch.from_numpy(g[k]) for k in ("structure_tokens", "sequence_tokens", "mask")}
+    for name, T in (("plain", 0), ("discrete_T", 50)):
+        m.T = T
+        torch.manual_seed(11)
+        loss, bd = m.model_step(batch, training=False)
+        want = float(g[f"{name}_loss"])
+        assert np.array_equal(bd["xt"].numpy(), g[f"{name}_xt"]) and np.array_equal(bd["t"].numpy(), g[f"{name}_t"])
+        print(f"[model_step {name}] nelbo {float(loss):.5f} vs reference {want:.5f} (rel {abs(float(loss) - want) / want:.2e})")
+        assert abs(float(loss) - want) / want < 2e-4          # measured 4.1e-5 / 7.6e-6 on B200
+
+
 def test_inpainting_tiny(tiny_pair):
     from esmdiff_b200.sampling import build_prior
     _, _, eng = tiny_pair
