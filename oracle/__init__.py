@@ -16,7 +16,11 @@ Contents
                  464-492, 527-607) and LogLinearNoise (slm/utils/noise_utils.py:188-213).
                  Pinned bit-for-bit against the reference's own code run in the build
                  container (``ref_loader`` + ``make_golden`` -> ``tests/golden/``).
+* ``geom_ref`` / ``vqvae_enc_ref`` / ``vqvae_ref`` / ``gibbs_ref``  restatements of the esm==3.0.4 pieces around the
+                 path: backbone frames + geometric attention, the VQ-VAE structure encoder and decoder, the
+                 iterative structure sampler (**parity unpinned**, each says so in its header).
 * ``ref_loader`` imports the reference's model.py / noise_utils.py verbatim through stub
                  modules.  Works only where /root/reference exists (the build container).
+* ``make_golden_model_step`` the reference's own ``model_step`` (forward half) -> ``tests/golden/model_step.npz``.
 * ``make_golden`` regenerates ``tests/golden/*.npz`` from the verbatim reference.
 """
