@@ -97,7 +97,12 @@ template <int EPI, int BN> struct Cfg {
     static constexpr int VEC_BYTES = EPI == EPI_QKV_ROPE_LN ? 3 * 128 * 4 : 0;
     static constexpr int STG_BYTES = EPI_WARPS * (BOXES * BOX_BYTES + VEC_BYTES);
     static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STG_BYTES) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_FIT < MAX_STAGES ? STAGES_FIT : MAX_STAGES;
+#ifdef ESMDIFF_STAGES_CAP                                   // experiment builds: cap the TMA ring depth (tools/kbench_qkv_variants.py)
+    static constexpr int STAGES_MAX_ = ESMDIFF_STAGES_CAP < MAX_STAGES ? ESMDIFF_STAGES_CAP : MAX_STAGES;
+#else
+    static constexpr int STAGES_MAX_ = MAX_STAGES;
+#endif
+    static constexpr int STAGES = STAGES_FIT < STAGES_MAX_ ? STAGES_FIT : STAGES_MAX_;
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + 512;
     static_assert(SMEM_BYTES <= 227 * 1024 && STAGES >= 4, "shared memory budget");
 };

@@ -16,6 +16,8 @@
 #include <cuda_bf16.h>
 #include <float.h>
 
+#include "ptx.cuh"
+
 namespace esmdiff {
 namespace geom {
 
@@ -154,7 +156,7 @@ rotate_kernel(const TIn* p, float* out, const float* __restrict__ rot, const flo
 //   out [M][ldo] (first 3 H columns): softmax-weighted values rotated back into the query's frame (R_i^T),
 //   zeroed for frameless queries when zero_frameless (TransformerStack(mask_and_zero_frameless=True)).
 template <int QPT, typename TOut>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 attention_kernel(const float* __restrict__ r, const float* __restrict__ rot, const unsigned char* __restrict__ mask,
                  const int* __restrict__ frame_idx, const float* __restrict__ w_rot, const float* __restrict__ w_dist,
                  TOut* __restrict__ out, int ldo, int S, int H, int zero_frameless) {
@@ -162,11 +164,12 @@ attention_kernel(const float* __restrict__ r, const float* __restrict__ rot, con
     const long long row0 = static_cast<long long>(blockIdx.y) * S;
     const int q0 = blockIdx.x * QPT;
     const long long ld = 15ll * H;
-    const float inv_sqrt3 = 0.57735026918962576f;
-    // softplus of the per-head scales (F.softplus, threshold 20)
+    // scores in the log2 domain: softplus of the per-head scales (F.softplus, threshold 20), 1/sqrt3 and log2(e)
+    // folded into two per-head factors; the +1 of esm's float same-sequence mask becomes + log2(e)
+    const float LOG2E = 1.4426950408889634f;
     const float wr_raw = w_rot[h], wd_raw = w_dist[h];
-    const float wr = (wr_raw > 20.f ? wr_raw : log1pf(expf(wr_raw)));
-    const float wd = (wd_raw > 20.f ? wd_raw : log1pf(expf(wd_raw)));
+    const float wr = (wr_raw > 20.f ? wr_raw : log1pf(expf(wr_raw))) * (0.57735026918962576f * LOG2E);
+    const float wd = (wd_raw > 20.f ? wd_raw : log1pf(expf(wd_raw))) * (0.57735026918962576f * LOG2E);
     float qr[QPT][3], qd[QPT][3], acc[QPT][3], mx[QPT], l[QPT];
 #pragma unroll
     for (int q = 0; q < QPT; ++q) {
@@ -181,27 +184,43 @@ attention_kernel(const float* __restrict__ r, const float* __restrict__ rot, con
         mx[q] = -INFINITY;
         l[q] = 0.f;
     }
-    for (int j = 0; j < S; ++j) {
+    // the key / value vectors of step j + 1 are fetched (L2) while step j is computed
+    float kv[9];
+    bool keyed_next;
+    auto fetch = [&](int j) {
         const float* base = r + (row0 + j) * ld;
-        const float k0 = base[3 * H + h * 3], k1 = base[3 * H + h * 3 + 1], k2 = base[3 * H + h * 3 + 2];
-        const float v0 = base[6 * H + h * 3], v1 = base[6 * H + h * 3 + 1], v2 = base[6 * H + h * 3 + 2];
-        const float d0 = base[12 * H + h * 3], d1 = base[12 * H + h * 3 + 1], d2 = base[12 * H + h * 3 + 2];
-        const long long fj = frame_idx ? frame_idx[row0 + j] : row0 + j;
-        const float bias = mask[fj] ? 1.0f : -FLT_MAX;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            kv[c] = base[3 * H + h * 3 + c];
+            kv[3 + c] = base[6 * H + h * 3 + c];
+            kv[6 + c] = base[12 * H + h * 3 + c];
+        }
+        keyed_next = mask[frame_idx ? frame_idx[row0 + j] : row0 + j] != 0;
+    };
+    fetch(0);
+    for (int j = 0; j < S; ++j) {
+        const float k0 = kv[0], k1 = kv[1], k2 = kv[2], v0 = kv[3], v1 = kv[4], v2 = kv[5], d0 = kv[6], d1 = kv[7], d2 = kv[8];
+        const bool keyed = keyed_next;
+        if (j + 1 < S) fetch(j + 1);
 #pragma unroll
         for (int q = 0; q < QPT; ++q) {
-            const float rt = (qr[q][0] * k0 + qr[q][1] * k1 + qr[q][2] * k2) * inv_sqrt3;
+            const float rt = qr[q][0] * k0 + qr[q][1] * k1 + qr[q][2] * k2;
             const float e0 = qd[q][0] - d0, e1 = qd[q][1] - d1, e2 = qd[q][2] - d2;
-            const float dt = sqrtf(e0 * e0 + e1 * e1 + e2 * e2) * inv_sqrt3;
-            const float w = (rt * wr - dt * wd) + bias;
-            const float mn = fmaxf(mx[q], w);
-            const float corr = expf(mx[q] - mn);          // first key: exp(-inf) = 0
-            const float pe = expf(w - mn);
-            l[q] = l[q] * corr + pe;
-            acc[q][0] = acc[q][0] * corr + pe * v0;
-            acc[q][1] = acc[q][1] * corr + pe * v1;
-            acc[q][2] = acc[q][2] * corr + pe * v2;
-            mx[q] = mn;
+            float dt;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(dt) : "f"(e0 * e0 + e1 * e1 + e2 * e2));
+            // a frameless key: score + finfo.min == finfo.min in fp32, whatever the score
+            const float w = keyed ? fmaf(rt, wr, fmaf(-dt, wd, LOG2E)) : -FLT_MAX;
+            if (w > mx[q]) {                                 // raise the running maximum (rare after the first keys)
+                const float corr = fast_exp2(mx[q] - w);     // first key: exp2(-inf) = 0
+                l[q] *= corr;
+                acc[q][0] *= corr; acc[q][1] *= corr; acc[q][2] *= corr;
+                mx[q] = w;
+            }
+            const float pe = fast_exp2(w - mx[q]);
+            l[q] += pe;
+            acc[q][0] = fmaf(pe, v0, acc[q][0]);
+            acc[q][1] = fmaf(pe, v1, acc[q][1]);
+            acc[q][2] = fmaf(pe, v2, acc[q][2]);
         }
     }
 #pragma unroll

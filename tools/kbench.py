@@ -222,11 +222,47 @@ def bench_qk(flush):
     e.close()
 
 
+def bench_enc(flush):
+    """Inpainting front end: the fp32 structure encoder (once per target) and what live geometric attention in
+    block 0 adds to a forward of the sampling network."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    from esmdiff_b200.encoder import load_encoder
+    from esmdiff_b200.synthetic import random_state_dict
+    from oracle.vqvae_enc_ref import synthetic_backbone
+    enc = load_encoder(None)
+    d = enc.dims
+    for L in (58, 256, 512, 1024):
+        bb = synthetic_backbone(L, seed=1)[None].to(dev)
+        ms = timeit(lambda: enc.encode(bb, return_aux=True), n=10, warm=3)
+        M = L * min(d.knn, L)
+        fl = 2.0 * M * d.n_layers * (d.d_model * 15 * d.v_heads + 3 * d.v_heads * d.d_model + 3 * d.d_model * d.ffn_hidden)
+        print(f"  encoder L={L:5d}: {ms:7.3f} ms  ({M} neighbourhood rows, {fl / 1e9:.1f} GFLOP in the fp32 GEMMs -> "
+              f"{fl / ms / 1e9:.1f} TFLOP/s overall)", flush=True)
+    e = Engine(Dims())
+    e.load_state_dict(random_state_dict(Dims(), device="cuda", seed=0, full=True))
+    for (B, T) in [(100, 258), (13, 258), (32, 514)]:
+        g = torch.Generator().manual_seed(0)
+        seq = torch.randint(4, 24, (B, T), generator=g).to(dev)
+        xt = torch.randint(0, 4096, (B, T), generator=g).to(dev)
+        coords = torch.full((B, T, 3, 3), float("nan"))
+        coords[:, 1:-1] = synthetic_backbone(T - 2, seed=2)
+        coords[:, 2:34] = float("inf")
+        logits = torch.empty(B, T, 4101, device=dev)
+        t0 = timeit(lambda: e.forward_sigma(seq, xt, 0.5, logits_out=logits), n=6, warm=2)
+        e.set_structure_coords(coords)
+        t1 = timeit(lambda: e.forward_sigma(seq, xt, 0.5, logits_out=logits), n=6, warm=2)
+        e.set_structure_coords(None)
+        keys = B * T * T * 256 * 36.0                       # bytes of rotated key / value vectors the attention walks / QPT
+        print(f"  forward B={B} T={T}: {t0:7.3f} ms, with structure_coords {t1:7.3f} ms (+{(t1 - t0) * 1e3:.0f} us, "
+              f"+{(t1 / t0 - 1) * 100:.2f} %); key-vector reads {keys / 8 / 1e9:.2f} GB at QPT = 8", flush=True)
+    e.close()
+
+
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0), flush=True)
     which = sys.argv[1:] or ["attn", "gemm", "rows"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
-    table = dict(gemm=bench_gemm, attn=bench_attn, attn_ln=bench_attn_ln, rows=bench_rows, qk=bench_qk)
+    table = dict(gemm=bench_gemm, attn=bench_attn, attn_ln=bench_attn_ln, rows=bench_rows, qk=bench_qk, enc=bench_enc)
     for wname in which:
         print(f"=== {wname} ===", flush=True)
         table[wname](flush)
