@@ -343,3 +343,38 @@ def test_network_forward_with_structure_coords_tiny():
           f"effect of the branch {effect:.3f}")
     assert e_ref < 8.5e-3 and e_emu < 6.4e-3 and effect > 0.05
     assert torch.equal(got[2], got0[2])                                   # frameless sample: bit-identical to no coordinates
+
+
+@pytest.mark.gpu
+def test_structure_coords_error_behaviour(tiny_pair):
+    """esmdiff_set_structure_coords: a context whose v_heads cannot run the branch refuses (the fixture's tiny net has
+    v_heads = 8: 3 v_heads % 64 != 0); a batch shape other than the one the coordinates were given for fails loudly
+    instead of reading frames of other rows; NULL switches the branch off again."""
+    from esmdiff_b200._lib import EsmdiffError
+    from esmdiff_b200.engine import Dims, Engine
+    from esmdiff_b200.synthetic import random_state_dict
+    _, _, eng8 = tiny_pair
+    with pytest.raises(EsmdiffError, match="v_heads"):
+        eng8.set_structure_coords(torch.zeros(2, 10, 3, 3))
+    dims = Dims(d_model=256, n_heads=4, v_heads=64, n_layers=2)
+    eng = Engine(dims)
+    sd = random_state_dict(dims, device=DEV, seed=0, full=False)          # a checkpoint WITHOUT the geom_attn.* keys
+    eng.load_state_dict(sd)
+    seq = torch.full((2, 20), 5)
+    xt = torch.full((2, 20), 4096)
+    eng.set_structure_coords(torch.zeros(2, 20, 3, 3))
+    with pytest.raises(EsmdiffError, match="geom_attn"):
+        eng.forward(seq, xt)
+    eng.set_structure_coords(None)
+    eng.forward(seq, xt)                                                 # fine again without coordinates
+    sd = random_state_dict(dims, device=DEV, seed=0, full=True)
+    eng.load_state_dict(sd)
+    base, _ = eng.forward(seq, xt)
+    eng.set_structure_coords(torch.zeros(2, 20, 3, 3))
+    with pytest.raises(EsmdiffError, match="batch shape"):
+        eng.forward(seq[:1], xt[:1])
+    eng.set_structure_coords(None)
+    again, _ = eng.forward(seq, xt)
+    eng.synchronize()
+    assert torch.equal(again, base)
+    eng.close()
