@@ -222,6 +222,11 @@ __device__ __forceinline__ void ld_uniform(float* r, const float* g) {
 // The same from shared memory (one broadcast read per 16 bytes).
 template <int N>
 __device__ __forceinline__ void ld_uniform_smem(float* r, const float* s) {
+#ifdef ESMDIFF_EXP_NOVEC                                    // timing experiment: no shared-memory broadcasts (results wrong)
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = 1.0f + 0.001f * i;
+    return;
+#endif
 #pragma unroll
     for (int i = 0; i < N / 4; ++i) {
         const float4 v = reinterpret_cast<const float4*>(s)[i];
@@ -555,7 +560,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         reinterpret_cast<float4*>(vec + 256)[lane] = g4;
                     }
                     __syncwarp();
+#ifdef ESMDIFF_EXP_NOTABLE                                  // timing experiment: no rotary table loads (results wrong)
+                    if (rot && rope_mt < 0) {
+#else
                     if (rot && mt != rope_mt) {
+#endif
                         const int row = row_base + lane < p.M ? row_base + lane : p.M - 1;
                         const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(row % p.T) * 64);
 #pragma unroll
