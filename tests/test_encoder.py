@@ -378,3 +378,55 @@ def test_structure_coords_error_behaviour(tiny_pair):
     eng.synchronize()
     assert torch.equal(again, base)
     eng.close()
+
+
+def test_sdk_protein_roundtrip_on_cpu(tmp_path):
+    """The esm SDK surface mirrors (esmdiff_b200/sdk.py): ESMProtein.to_pdb -> from_pdb gives the backbone back (PDB
+    precision), '_' residues are written as UNK / read as X, ESMProteinTensor.to and len behave like esm's."""
+    from esmdiff_b200.sdk import ESMProtein, ESMProteinTensor
+    bb = V.synthetic_backbone(7, seed=2)
+    coords = torch.full((7, 37, 3), float("nan"))
+    coords[:, :3] = bb
+    coords[:, 4] = bb[:, 2] + torch.tensor([0.5, -1.0, 0.2])
+    coords[6, 4] = float("nan")                                           # the last residue has no O (infer_oxygen)
+    prot = ESMProtein(sequence="ACD_FGH", coordinates=coords, plddt=torch.linspace(0.1, 0.9, 7))
+    assert len(prot) == 7
+    prot.to_pdb(tmp_path / "p.pdb")
+    text = (tmp_path / "p.pdb").read_text().splitlines()
+    assert all(len(ln) == 80 for ln in text) and text[-1].strip() == "END" and text[-2].startswith("TER")
+    assert sum(ln.startswith("ATOM") for ln in text) == 7 * 4 - 1
+    back = ESMProtein.from_pdb(tmp_path / "p.pdb")
+    assert back.sequence == "ACDXFGH"
+    assert torch.allclose(back.coordinates[:, :3], bb, atol=1e-3) and torch.isnan(back.coordinates[6, 4]).all()
+    assert abs(float(text[0][60:66]) - 0.1) < 0.006                        # pLDDT in the B-factor column
+    t = ESMProteinTensor(sequence=torch.arange(9), structure=None)
+    assert len(t) == 9 and t.to("cpu").structure is None and torch.equal(t.to("cpu").sequence, t.sequence)
+
+
+@pytest.mark.gpu
+def test_sdk_surface_runs_the_reference_helpers(tmp_path):
+    """esm3_model.encode(ESMProtein(sequence, coordinates)) (models/utils.py:136-137) and the reference's per-sample
+    decode(structure_tokens, sequence_tokens, esm3_model, save_to) (sample_esmdiff.py:41-61) through the SDK mirror:
+    tokens equal protseq_to_data's, the PDB equals MODEL 1 of the batched writer's file."""
+    from esmdiff_b200 import sdk
+    from esmdiff_b200.decoder import decode_to_pdb, load_decoder
+    from esmdiff_b200.encoder import load_encoder, protseq_to_data
+    from esmdiff_b200.tokenization import tokenize_sequence
+    write_backbone_pdb(tmp_path / "bpti.pdb", BPTI, V.synthetic_backbone(len(BPTI), seed=4))
+    prot = sdk.ESMProtein.from_pdb(tmp_path / "bpti.pdb")
+    assert prot.sequence == BPTI and prot.coordinates.shape == (len(BPTI), 37, 3)
+    esm3 = sdk.ESM3(structure_encoder=load_encoder(None), structure_decoder=load_decoder(None))
+    masked = sdk.ESMProtein(sequence=BPTI[:2] + "__" + BPTI[4:], coordinates=prot.coordinates.clone())
+    masked.coordinates[2:4] = float("inf")
+    toks = esm3.encode(masked)
+    want = protseq_to_data(BPTI, esm3.get_structure_encoder(), encode_only=True, coordinates=prot.coordinates, mask_ids=[2, 3])
+    assert torch.equal(toks.sequence, want["sequence_tokens"]) and torch.equal(toks.structure, want["structure_tokens"])
+    assert toks.coordinates.shape == (len(BPTI) + 2, 37, 3) and torch.isinf(toks.coordinates[0]).all()
+    assert len(toks) == len(BPTI) + 2 and toks.to(DEV).structure.is_cuda
+    st = toks.structure[1:-1]
+    raw = sdk.decode(st, tokenize_sequence(BPTI)[1:-1], esm3, save_to=tmp_path / "one.pdb")
+    assert raw.sequence == BPTI and raw.coordinates.shape == (len(BPTI), 37, 3)
+    decode_to_pdb(esm3.get_structure_decoder(), st[None], BPTI, tmp_path / "batched.pdb")
+    one = [ln for ln in (tmp_path / "one.pdb").read_text().splitlines() if ln.startswith(("ATOM", "TER"))]
+    bat = [ln for ln in (tmp_path / "batched.pdb").read_text().splitlines() if ln.startswith(("ATOM", "TER"))]
+    assert one == bat and len(one) == 4 * len(BPTI) - 1 + 1
