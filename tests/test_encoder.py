@@ -430,3 +430,52 @@ def test_sdk_surface_runs_the_reference_helpers(tmp_path):
     one = [ln for ln in (tmp_path / "one.pdb").read_text().splitlines() if ln.startswith(("ATOM", "TER"))]
     bat = [ln for ln in (tmp_path / "batched.pdb").read_text().splitlines() if ln.startswith(("ATOM", "TER"))]
     assert one == bat and len(one) == 4 * len(BPTI) - 1 + 1
+
+
+def test_frames_and_atom37_against_installed_openfold_utils():
+    """Second anchors for the unpinned restatements, from code that IS installed here: transformers ships the
+    OpenFold utilities ESMFold uses, and esm's ``Affine3D.from_graham_schmidt(neg_x_axis, origin, xy_plane)`` states
+    it follows AlphaFold's argument convention -- OpenFold's ``Rigid.from_3_points(p_neg_x_axis, origin, p_xy_plane)``
+    is that construction.  The oracle's backbone frames (C, CA, N) must equal it; the atom37 order and the
+    three-letter table of the PDB reader must equal ``residue_constants``."""
+    rc = pytest.importorskip("transformers.models.esm.openfold_utils.residue_constants")
+    ru = pytest.importorskip("transformers.models.esm.openfold_utils.rigid_utils")
+    from esmdiff_b200.decoder import ONE_TO_THREE
+    from esmdiff_b200.encoder import ATOM37
+    from esmdiff_b200.tokenization import THREE_TO_ONE
+    assert list(ATOM37) == list(rc.atom_types)
+    for one, three in rc.restype_1to3.items():
+        assert THREE_TO_ONE[three] == one and ONE_TO_THREE[one] == three
+    bb = V.synthetic_backbone(50, seed=9)
+    rot, trans = geom_ref.backbone_frames(bb)
+    rigid = ru.Rigid.from_3_points(bb[:, 2], bb[:, 1], bb[:, 0], eps=1e-12)
+    assert torch.allclose(rigid.get_rots().get_rot_mats(), rot, atol=2e-6)
+    assert torch.equal(rigid.get_trans(), trans)
+    # and the decoder side: Dim6RotStructureHead's frame from (trans, x, y) is the same construction
+    from oracle import vqvae_ref
+    x, y, t = torch.randn(20, 3), torch.randn(20, 3), torch.randn(20, 3)
+    want = ru.Rigid.from_3_points(x + t, t, y + t, eps=1e-12).get_rots().get_rot_mats()
+    assert torch.allclose(vqvae_ref.graham_schmidt(t - (x + t), (y + t) - t, 1e-12), want, atol=2e-5)
+
+
+def test_ideal_backbone_constants_against_literature_positions():
+    """esm's BB_COORDINATES (the residue-frame N, CA, C the decoder places, oracle/vqvae_ref.py) are the AlphaFold
+    literature positions with the x axis flipped (esm's frame points from C to CA): within 0.01 A of
+    residue_constants.rigid_group_atom_positions averaged over the 20 residue types; the carbonyl O vector of
+    infer_oxygen has the literature C=O length and direction (psi-frame (0.626, 1.062, 0), y flipped)."""
+    rc = pytest.importorskip("transformers.models.esm.openfold_utils.residue_constants")
+    from oracle import vqvae_ref
+    pos = {a: [] for a in ("N", "CA", "C")}
+    o = []
+    for res, atoms in rc.rigid_group_atom_positions.items():
+        for name, group, xyz in atoms:
+            if name in pos and group == 0:
+                pos[name].append(xyz)
+            if name == "O":
+                o.append(xyz)
+    lit = torch.tensor([[sum(c) / len(c) for c in zip(*pos[a])] for a in ("N", "CA", "C")])
+    lit[:, 0] *= -1
+    assert float((torch.tensor(vqvae_ref.BB_COORDINATES) - lit).abs().max()) < 0.012
+    o_lit = torch.tensor([sum(c) / len(c) for c in zip(*o)])
+    o_esm = torch.tensor(vqvae_ref.O_VECTOR)
+    assert abs(float(o_esm.norm() - o_lit.norm())) < 0.01 and float((o_esm - o_lit * torch.tensor([1.0, -1.0, 1.0])).abs().max()) < 0.02
