@@ -117,6 +117,11 @@ struct esmdiff_ctx {
                                // B=100, T=258: strided 234 us, runs of 2 / 3 / 6 column tiles 243 / 255 / 290 us, contiguous ranges
                                // 263 us -- re-reading the rotary table row per tile is cheaper than any loss of L2 locality
                                // or balance); ESMDIFF_QKV_RUN overrides
+    bool skip_denoise = false; // ESMDIFF_SKIP_DENOISE_FORWARD=1: esmdiff_ddpm_sample leaves out the noise-removal forward when no
+                               // MASK is left after the last step (exact: unmasked rows return themselves, model.py:575-579;
+                               // SURVEY.md section 7 step 6).  Costs one stream synchronisation; off by default -- the
+                               // benchmark runs the reference's 26 forwards
+    int* dev_count = nullptr;
     bool pdl = true;           // programmatic dependent launch between the kernels of a forward; ESMDIFF_PDL=0 -> off
     bool qk_fused = true;      // q_ln / k_ln + RoPE folded into the QKV epilogue and the attention kernel
                                // (needs ln_fold); ESMDIFF_QK=separate -> stand-alone ew::qk_layernorm_rope_kernel
@@ -769,6 +774,13 @@ __global__ void fill_i64_kernel(long long* p, long long v, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
+// number of entries equal to `v` (is a MASK left before the noise-removal forward?)
+__global__ void count_equal_kernel(const long long* p, long long v, long long n, int* count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool hit = i < n && p[i] == v;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
 __global__ void bf16_to_f32_kernel(const bf16* s, float* d, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = __bfloat162float(s[i]);
@@ -981,6 +993,7 @@ int esmdiff_create(const esmdiff_cfg* cfg, int device, esmdiff_ctx** out) {
     if (const char* e = getenv("ESMDIFF_LN")) c->ln_fold = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_QK")) c->qk_fused = strcmp(e, "separate") != 0;
     if (const char* e = getenv("ESMDIFF_PDL")) c->pdl = atoi(e) != 0;
+    if (const char* e = getenv("ESMDIFF_SKIP_DENOISE_FORWARD")) c->skip_denoise = atoi(e) != 0;
     if (const char* e = getenv("ESMDIFF_QKV_RUN")) c->qkv_run = atoi(e);
     if (const char* e = getenv("ESMDIFF_SPLIT_ROWS")) c->split_rows = atoll(e);
     if (const char* e = getenv("ESMDIFF_RESID_BN")) c->resid_bn = atoi(e);
@@ -1309,6 +1322,18 @@ int esmdiff_ddpm_sample(esmdiff_ctx* c, const int64_t* seq, const int64_t* prior
     }
     const int total = steps + (noise_removal ? 1 : 0);
     for (int i = 0; i < total; ++i) {               // step-major enqueue: both chains stay fed even without graphs
+        if (i == steps && c->skip_denoise && nparts == 1) {
+            // noise removal only rewrites rows that still hold a MASK: none left -> the forward is dead work
+            if (!c->dev_count && c->alloc(&c->dev_count, 1)) return 1;
+            CK(cudaMemsetAsync(c->dev_count, 0, sizeof(int), st));
+            count_equal_kernel<<<(M + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(out),
+                                                                ESMDIFF_STRUCTURE_MASK_TOKEN, M, c->dev_count);
+            c->launches++;
+            int left = 1;
+            CK(cudaMemcpyAsync(&left, c->dev_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (left == 0) break;
+        }
         for (int h = 0; h < nparts; ++h) {
             const Part& pt = parts[h];
             if (c->activate(h) || ensure_workspace(c, (int64_t)pt.nb * T)) { c->activate(0); return 1; }

@@ -559,3 +559,36 @@ def test_two_stream_half_batches_are_bit_identical():
     for a, b, c in zip(outs["single"], outs["split"], outs["split_eager"]):
         assert torch.equal(a, b) and torch.equal(a, c)
         assert a.dtype != torch.int64 or int((a == MASK).sum()) == 0
+
+
+def test_skip_of_dead_noise_removal_forward_is_exact(monkeypatch):
+    """SURVEY.md section 7 step 6 (optional, off by default): with ESMDIFF_SKIP_DENOISE_FORWARD=1 the device loop leaves
+    out the noise-removal forward when no MASK is left after the last step -- unmasked rows return themselves
+    (model.py:575-579), so the tokens are bit-identical and a forward's worth of launches is saved; with a MASK left
+    it runs as usual."""
+    from conftest import TINY
+    from esmdiff_b200.engine import Dims, Engine
+    net, emb = esm3_ref.build_reference_model(esm3_ref.Esm3Dims(**TINY), seed=0)
+    sd = esm3_ref.full_state_dict(net, emb)
+    seq = make_seq(6, 40, seed=4)
+    outs, launches = {}, {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ESMDIFF_SKIP_DENOISE_FORWARD", flag)
+        eng = Engine(Dims(**TINY))
+        eng.load_state_dict(sd)
+        sigma, mc_t, mc_s = eng.schedule(12)
+        res = []
+        for case, last_mc_s in (("none_left", 0.0), ("some_left", 0.5)):
+            mcs = list(mc_s)
+            mcs[-1] = last_mc_s                      # chance to stay masked after the last step: 0 -> every row is revealed
+            l0 = eng.launch_count
+            res.append(eng.ddpm_sample(seq, None, 12, sigma, mc_t, mcs, seed=3).cpu())
+            eng.synchronize()
+            launches[(flag, case)] = eng.launch_count - l0
+        outs[flag] = res
+        eng.close()
+    assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+    assert int((outs["1"][0] == MASK).sum()) == 0 and int((outs["1"][1] == MASK).sum()) == 0
+    saved = launches[("0", "none_left")] - launches[("1", "none_left")]
+    assert saved > 10, launches                                              # one forward (2 blocks + head) not launched
+    assert launches[("1", "some_left")] == launches[("0", "some_left")] + 1  # only the counting kernel added
