@@ -84,6 +84,100 @@ def pdb_model_lines(sequence: str, bb: np.ndarray, o: np.ndarray, plddt: np.ndar
     return lines
 
 
+def _fixed_width(x: np.ndarray, width: int, dec: int) -> np.ndarray:
+    """Vectorised ``f"{x:{width}.{dec}f}"`` for float32-valued x: (n,) -> (n, width) uint8.  x * 10^dec is exact in
+    float64 for float32 inputs, so rint (ties to even) is the correctly rounded decimal Python prints."""
+    x = x.astype(np.float64)
+    v = np.abs(np.rint(x * 10 ** dec)).astype(np.int64)
+    neg = np.signbit(x)
+    n = x.shape[0]
+    out = np.full((n, width), 32, np.uint8)
+    a = v.copy()
+    for k in range(dec):
+        out[:, width - 1 - k] = 48 + a % 10
+        a //= 10
+    out[:, width - 1 - dec] = 46
+    pos = width - 2 - dec
+    out[:, pos] = 48 + a % 10
+    a //= 10
+    nd = np.ones(n, np.int64)
+    while pos > 0 and bool((a > 0).any()):
+        pos -= 1
+        nz = a > 0
+        out[nz, pos] = 48 + a[nz] % 10
+        nd += nz
+        a //= 10
+    assert not bool((a > 0).any()), "value too wide for the PDB column"
+    sp = width - 2 - dec - nd
+    assert not bool((neg & (sp < 0)).any()), "value too wide for the PDB column"
+    rows = np.nonzero(neg)[0]
+    out[rows, sp[rows]] = 45
+    return out
+
+
+def _int_width(v: np.ndarray, width: int) -> np.ndarray:
+    """Vectorised ``f"{v:{width}d}"`` for non-negative ints."""
+    n = v.shape[0]
+    out = np.full((n, width), 32, np.uint8)
+    a = v.astype(np.int64).copy()
+    out[:, width - 1] = 48 + a % 10
+    a //= 10
+    pos = width - 1
+    while pos > 0 and bool((a > 0).any()):
+        pos -= 1
+        nz = a > 0
+        out[nz, pos] = 48 + a[nz] % 10
+        a //= 10
+    assert not bool((a > 0).any())
+    return out
+
+
+def pdb_models_text(sequence: str, bb: np.ndarray, o: np.ndarray, plddt: np.ndarray | None) -> str:
+    """The whole multi-MODEL file of ``decode_to_pdb`` in one vectorised pass (bb (N, L, 3, 3), o (N, L, 3),
+    plddt (N, L) or None): byte for byte what ``pdb_model_lines`` + the MODEL / ENDMDL / END framing give, ~10x faster --
+    at 100 samples x 256 residues the per-line f-strings cost 0.6 s against 1.8 s of sampling."""
+    N, L = bb.shape[:2]
+    xyz = np.concatenate([bb.reshape(N, L, 3, 3), o.reshape(N, L, 1, 3)], axis=2).astype(np.float32)   # (N, L, 4, 3)
+    fin = np.where(np.isfinite(xyz), xyz, 0.0)
+    if float(fin.max(initial=0.0)) >= 9999.9995 or float(fin.min(initial=0.0)) <= -999.9995:
+        raise ValueError("coordinates too wide for the 8.3f PDB columns")
+    valid = np.isfinite(xyz).all(-1)                                             # (N, L, 4)
+    res3 = np.array([list(ONE_TO_THREE.get(a, "UNK").rjust(3).encode()) for a in sequence], np.uint8)           # (L, 3)
+    names = np.array([list(f"{nm:<3s}".encode()) for nm in ATOM_NAMES], np.uint8)                               # (4, 3)
+    elem = np.array([ord(nm[0]) for nm in ATOM_NAMES], np.uint8)
+    b = np.zeros((N, L), np.float32) if plddt is None else plddt.astype(np.float32)
+    serial = np.cumsum(valid.reshape(N, -1), axis=1).reshape(N, L, 4)
+    n_idx, l_idx, a_idx = np.nonzero(valid)
+    cnt = n_idx.shape[0]
+    rows = np.full((cnt, 81), 32, np.uint8)
+    rows[:, 80] = 10
+    rows[:, 0:6] = np.frombuffer(b"ATOM  ", np.uint8)
+    rows[:, 6:11] = _int_width(serial[n_idx, l_idx, a_idx], 5)
+    rows[:, 13:16] = names[a_idx]
+    rows[:, 17:20] = res3[l_idx]
+    rows[:, 21] = 65
+    rows[:, 22:26] = _int_width(l_idx + 1, 4)
+    for k in range(3):
+        rows[:, 30 + 8 * k:38 + 8 * k] = _fixed_width(xyz[n_idx, l_idx, a_idx, k], 8, 3)
+    rows[:, 54:60] = np.frombuffer(b"  1.00", np.uint8)
+    rows[:, 60:66] = _fixed_width(b[n_idx, l_idx], 6, 2)
+    rows[:, 77] = elem[a_idx]
+    per_model = valid.reshape(N, -1).sum(1)
+    ends = np.cumsum(per_model)
+    buf = rows.tobytes()
+    parts = []
+    for n in range(N):
+        parts.append(f"MODEL     {n + 1}".ljust(80) + "\n")
+        lo, hi = int(ends[n] - per_model[n]), int(ends[n])
+        parts.append(buf[lo * 81:hi * 81].decode())
+        if hi > lo:
+            last_l = int(l_idx[hi - 1])
+            parts.append(f"TER   {int(per_model[n]) + 1:5d}      {ONE_TO_THREE.get(sequence[last_l], 'UNK'):>3s} A{last_l + 1:4d}".ljust(80) + "\n")
+        parts.append("ENDMDL".ljust(80) + "\n")
+    parts.append("END".ljust(80) + "\n")
+    return "".join(parts)
+
+
 @torch.no_grad()
 def decode_to_pdb(decoder: StructureTokenDecoder, structure_tokens: torch.Tensor, sequence: str, save_to: Path,
                   max_tokens_per_batch: int = 1 << 17):
@@ -107,15 +201,9 @@ def decode_to_pdb(decoder: StructureTokenDecoder, structure_tokens: torch.Tensor
     bb = torch.cat(bbs).cpu().numpy()
     ox = torch.cat(os_).cpu().numpy()
     pl = torch.cat(pls).cpu().numpy() if pls else None
-    lines = []
-    for n in range(N):
-        lines.append(f"MODEL     {n + 1}")
-        lines += [ln.strip() for ln in pdb_model_lines(sequence, bb[n], ox[n], pl[n] if pl is not None else None)]
-        lines.append("ENDMDL")
-    lines.append("END")
     save_to = Path(save_to)
     save_to.parent.mkdir(parents=True, exist_ok=True)
-    save_to.write_text("\n".join(ln.ljust(80) for ln in lines) + "\n")
+    save_to.write_text(pdb_models_text(sequence, bb, ox, pl))
     return bb, pl
 
 

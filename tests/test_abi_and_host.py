@@ -356,3 +356,33 @@ def test_model_step_noise_draws_are_the_reference_ops(golden_dir):
         assert cs is seq                                          # coupled_condition_mask off: the sequence is untouched
     strata = np.floor(g["plain_t"] * 4 - 1e-3 * 4 * 0)            # antithetic sampling: one draw per quarter of [eps, 1)
     assert sorted(np.floor((g["plain_t"] - 1e-3) / (1 - 1e-3) * 4).astype(int).tolist()) == [0, 1, 2, 3]
+
+
+def test_vectorised_pdb_writer_equals_the_line_writer():
+    """decoder.pdb_models_text (one numpy pass over all samples) must give, byte for byte, what the per-line writer
+    (pdb_model_lines + MODEL / ENDMDL / END framing, the layout pinned by test_pdb_writer_layout) gives: signs of
+    negative zeros, ties, missing atoms, a model without the last O, unknown residues."""
+    from esmdiff_b200.decoder import pdb_model_lines, pdb_models_text
+    rng = np.random.default_rng(0)
+    N, L = 4, 23
+    seq = "".join(rng.choice(list("ACDEFGHIKLMNPQRSTVWY_X"), L))
+    bb = (rng.standard_normal((N, L, 3, 3)) * 40).astype(np.float32)
+    ox = (rng.standard_normal((N, L, 3)) * 40).astype(np.float32)
+    pl = rng.random((N, L)).astype(np.float32)
+    ox[:, -1] = np.nan
+    bb[0, 2, 1] = np.nan
+    bb[1, 0, 0] = [-0.0004, -0.0, 0.0005]
+    bb[1, 1, 0] = [999.9994, -99.9996, 0.0015]
+    bb[1, 2, 0] = [0.0025, 2.5e-4, -7.5e-4]
+    bb[2, 3], ox[2, 3] = np.nan, np.nan
+    pl[3, 0], pl[3, 1] = 0.005, 0.995
+    for plddt in (pl, None):
+        lines = []
+        for n in range(N):
+            lines.append(f"MODEL     {n + 1}")
+            lines += [ln.strip() for ln in pdb_model_lines(seq, bb[n], ox[n], None if plddt is None else plddt[n])]
+            lines.append("ENDMDL")
+        lines.append("END")
+        assert pdb_models_text(seq, bb, ox, plddt) == "\n".join(ln.ljust(80) for ln in lines) + "\n"
+    with pytest.raises(ValueError):
+        pdb_models_text(seq, bb * 1000, ox, pl)
