@@ -348,6 +348,8 @@ def _case(name):
         seq = tokenize_sequence(BPTI)[None].repeat(4, 1)
     elif name == "config3_B1_T514":
         seq = make_seq(1, 514, seed=3)
+    elif name == "config5_B1_T1026":
+        seq = make_seq(1, 1026, seed=5)
     else:
         seq = make_seq(2, 258, seed=1)
     B, T = seq.shape
@@ -368,12 +370,13 @@ def _case(name):
 
 
 @pytest.mark.parametrize("name", ["config1_bpti_B4_T60", "config2_B2_T258", "config3_B1_T514",
-                                  "config4_inpaint_B2_T258"])
+                                  "config4_inpaint_B2_T258", "config5_B1_T1026"])
 def test_full_size_forward_vs_oracles(full_model, full_oracle, name):
     """T2 at the real architecture (d=1536, 48 blocks, 24 heads) and at the sequence lengths of
     every BASELINE configuration: T = 60 (one partial query tile), T = 258 (two query tiles + the
     two CUDA-core trailing rows, five K/V tiles, 8-9 GEMM row tiles) and T = 514 (four query tiles,
-    nine K/V tiles); config 4's partially masked prior with masked sequence residues."""
+    nine K/V tiles); config 4's partially masked prior with masked sequence residues; config 5's longest chain,
+    T = 1026: the STREAMING attention kernel (K/V no longer resident in shared memory) inside the full forward."""
     eng, _ = full_model
     net, emb = full_oracle
     seq, xt, sigma = _case(name)
