@@ -386,3 +386,21 @@ def test_vectorised_pdb_writer_equals_the_line_writer():
         assert pdb_models_text(seq, bb, ox, plddt) == "\n".join(ln.ljust(80) for ln in lines) + "\n"
     with pytest.raises(ValueError):
         pdb_models_text(seq, bb * 1000, ox, pl)
+
+
+def test_every_noise_schedule_matches_the_reference_golden(golden_dir):
+    """All five schedules of slm/utils/noise_utils.py:122-213 (values frozen from the verbatim reference by
+    oracle/make_golden_noise.py): total noise, rate and the importance-sampling transformation, bit for bit."""
+    from esmdiff_b200 import noise_utils as nu
+    g = np.load(golden_dir / "noise_schedules.npz")
+    t, ti = torch.from_numpy(g["t"]), torch.from_numpy(g["t_importance"])
+    cases = {"LogLinearNoise": {}, "CosineNoise": {}, "CosineSqrNoise": {}, "Linear": {"sigma_min": 0.01, "sigma_max": 8.0},
+             "GeometricNoise": {"sigma_min": 1e-3, "sigma_max": 2.0}}
+    assert set(cases) == set(nu.SCHEDULES)
+    for name, kw in cases.items():
+        n = nu.SCHEDULES[name](**kw)
+        total, rate = n(t)
+        assert np.array_equal(total.numpy(), g[f"{name}_total"]), name
+        assert np.allclose((rate * torch.ones_like(t)).numpy(), g[f"{name}_rate"], rtol=2e-7, atol=0), name
+        if f"{name}_importance" in g:
+            assert np.array_equal(n.importance_sampling_transformation(ti).numpy(), g[f"{name}_importance"]), name
