@@ -344,14 +344,20 @@ def test_model_step_noise_draws_are_the_reference_ops(golden_dir):
     m = MaskedDiffusionLanguageModeling(net=None, noise_schedule=noise_utils.LogLinearNoise(), time_conditioning=True,
                                         condition_mask_rate=0.0)
     x0, seq = torch.from_numpy(g["structure_tokens"]), torch.from_numpy(g["sequence_tokens"])
-    for name, T in (("plain", 0), ("discrete_T", 50)):
+    for name, T in (("plain", 0), ("discrete_T", 50), ("importance", 0), ("change_of_variables", 0)):
+        m.importance_sampling = name == "importance"
         torch.manual_seed(11)
         t = m._sample_t(x0.shape[0], x0.device)
         if T > 0:
             t = (t * T).to(torch.int) / T
             t += 1 / T
-        sigma, _ = m.noise(t)
-        xt, cs = m.q_xt(x0.clone(), 1 - torch.exp(-sigma[:, None]), condition_seq=seq)
+        if name == "change_of_variables":
+            f_T = torch.log1p(- torch.exp(- m.noise.sigma_max))
+            f_0 = torch.log1p(- torch.exp(- m.noise.sigma_min))
+            move = torch.exp(f_0 + t * (f_T - f_0))[:, None]
+        else:
+            move = 1 - torch.exp(-m.noise(t)[0][:, None])
+        xt, cs = m.q_xt(x0.clone(), move, condition_seq=seq)
         assert np.array_equal(t.numpy(), g[f"{name}_t"]) and np.array_equal(xt.numpy(), g[f"{name}_xt"])
         assert cs is seq                                          # coupled_condition_mask off: the sequence is untouched
     strata = np.floor(g["plain_t"] * 4 - 1e-3 * 4 * 0)            # antithetic sampling: one draw per quarter of [eps, 1)
