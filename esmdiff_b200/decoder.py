@@ -174,6 +174,7 @@ def pdb_models_text(sequence: str, bb: np.ndarray, o: np.ndarray, plddt: np.ndar
             last_l = int(l_idx[hi - 1])
             parts.append(f"TER   {int(per_model[n]) + 1:5d}      {ONE_TO_THREE.get(sequence[last_l], 'UNK'):>3s} A{last_l + 1:4d}".ljust(80) + "\n")
         parts.append("ENDMDL".ljust(80) + "\n")
+    parts.append("ENDMDL".ljust(80) + "\n")          # merge_pdbfiles closes once more after the last model (eval_utils.py:484)
     parts.append("END".ljust(80) + "\n")
     return "".join(parts)
 
@@ -183,7 +184,7 @@ def decode_to_pdb(decoder: StructureTokenDecoder, structure_tokens: torch.Tensor
                   max_tokens_per_batch: int = 1 << 17):
     """structure_tokens (N, L) WITHOUT BOS/EOS (what the sampler returns, sample_esmdiff.py:217-221)
     -> one multi-MODEL PDB at ``save_to`` in the layout of the reference's ``merge_pdbfiles``
-    (MODEL n / ATOM ... / TER / ENDMDL per sample, END, lines padded to 80 columns).
+    (MODEL n / ATOM ... / TER / ENDMDL per sample, a closing ENDMDL, END, lines padded to 80 columns).
     Returns (bb (N,L,3,3), plddt (N,L)) on the host."""
     N, L = structure_tokens.shape
     assert L == len(sequence), f"{L} structure tokens for a sequence of {len(sequence)} residues"

@@ -101,6 +101,12 @@ def gibbs_sample_structure_tokens(net, sequence_tokens_singleton: torch.Tensor, 
     return tokens, time() - start_t
 
 
+def _timer(func):
+    from .sample_esmdiff import timer              # lazy: sample_esmdiff imports this module's functions lazily too
+    return timer(func)
+
+
+@_timer
 @torch.no_grad()
 def minibatch_gibbs_by_esm(protseq, esm3_model, output_dir: Path, sample_basename: str, num_samples: int = 10,
                            num_steps: int = 16, temperature: float = 1.4, top_p: float = 0.9,

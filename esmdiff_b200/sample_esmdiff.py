@@ -59,20 +59,42 @@ def _decode_with_esm(structure_tokens, sequence_tokens, save_paths):
         esm3.decode(ESMProteinTensor(sequence=seq, structure=s).to(dev)).to_pdb(path)
 
 
+def timer(func):
+    """eval_utils.py:24-34: prints ``Elapsed time (name): x.xx sec`` when the call returned something.  The reference's
+    wrapper also re-packs the result as ``(*result, elapsed)``; its callers ignore the value, so this one returns the
+    function's own result."""
+    import functools
+
+    @functools.wraps(func)
+    def wrapper(*args, **kwargs):
+        start_time = time()
+        result = func(*args, **kwargs)
+        if result is None:
+            return None
+        if kwargs.get("rank", 0) == 0:
+            print(f"Elapsed time ({func.__name__}): {time() - start_time:.2f} sec")
+        return result
+    return wrapper
+
+
 def merge_pdbfiles(pdb_files, save_to: Path):
     """Ordered merge into one multi-MODEL file (behaviour of eval_utils.py:437-492 for
-    single-model inputs, which is all the CLI produces)."""
+    single-model inputs, which is all the CLI produces -- including the closing ENDMDL the reference
+    appends after the last model's own: the file ends ENDMDL / ENDMDL / END; pinned by
+    tests/golden/merged_models.pdb, the reference function's own output)."""
     lines, n = [], 0
     for f in pdb_files:
         n += 1
         lines.append(f"MODEL     {n}")
         lines += [ln.strip() for ln in Path(f).read_text().splitlines() if ln.startswith(("TER", "ATOM"))]
         lines.append("ENDMDL")
+    lines.append("ENDMDL")
     lines.append("END")
     save_to.parent.mkdir(parents=True, exist_ok=True)
     save_to.write_text("\n".join(ln.ljust(80) for ln in lines) + "\n")
 
 
+@timer
 @torch.no_grad()
 def ddpm_sample_by_esm(sequence, pl_model, output_dir: Path, sample_basename: str, num_samples=5,
                        num_steps=10, eps=1e-5, mask_ids=None, structure_tokens=None, sample_max_t=1.0,

@@ -274,7 +274,7 @@ def test_cli_surface():
         assert tokenize_sequence("RPD_").tolist() == [0, 10, 14, 13, 32, 2]
         merge_pdbfiles([d / "a.pdb", d / "a.pdb"], d / "m.pdb")
         txt = (d / "m.pdb").read_text()
-        assert txt.count("MODEL") == 2 and txt.count("ENDMDL") == 2 and txt.rstrip().endswith("END")
+        assert txt.count("MODEL ") == 2 and txt.count("ENDMDL") == 3 and txt.rstrip().endswith("END")
     bpti = Path("/root/reference/data/targets/bpti/bpti.pdb")
     if bpti.exists():
         assert sequence_from_pdb(bpti) == "RPDFCLEPPYTGPCKARIIRYFYNAKAGLCQTFVYGGCRAKRNNFKSAEDCMRTCGGA"
@@ -388,7 +388,7 @@ def test_vectorised_pdb_writer_equals_the_line_writer():
             lines.append(f"MODEL     {n + 1}")
             lines += [ln.strip() for ln in pdb_model_lines(seq, bb[n], ox[n], None if plddt is None else plddt[n])]
             lines.append("ENDMDL")
-        lines.append("END")
+        lines += ["ENDMDL", "END"]
         assert pdb_models_text(seq, bb, ox, plddt) == "\n".join(ln.ljust(80) for ln in lines) + "\n"
     with pytest.raises(ValueError):
         pdb_models_text(seq, bb * 1000, ox, pl)
@@ -410,3 +410,30 @@ def test_every_noise_schedule_matches_the_reference_golden(golden_dir):
         assert np.allclose((rate * torch.ones_like(t)).numpy(), g[f"{name}_rate"], rtol=2e-7, atol=0), name
         if f"{name}_importance" in g:
             assert np.array_equal(n.importance_sampling_transformation(ti).numpy(), g[f"{name}_importance"]), name
+
+
+def test_multi_model_file_equals_the_reference_merge(golden_dir, tmp_path):
+    """tests/golden/merged_models.pdb is the output of the reference's OWN merge_pdbfiles (eval_utils.py:437-492,
+    exec'd from its source by oracle/make_golden_merge.py) on three single-model files.  Both writers of this package
+    -- the merge of per-sample files and the vectorised batch writer -- must reproduce it byte for byte, the
+    reference's closing ENDMDL after the last model included."""
+    from esmdiff_b200.decoder import pdb_models_text
+    from esmdiff_b200.sample_esmdiff import merge_pdbfiles
+    from oracle.make_golden_merge import inputs
+    want = (golden_dir / "merged_models.pdb").read_text()
+    assert want.splitlines()[-3:] == ["ENDMDL".ljust(80), "ENDMDL".ljust(80), "END".ljust(80)]
+    files, bbs, oxs = [], [], []
+    for i, (seq, bb, o, text) in enumerate(inputs()):
+        f = tmp_path / f"s.{i}.pdb"
+        f.write_text(text)
+        files.append(f)
+        bbs.append(bb)
+        oxs.append(o)
+    merge_pdbfiles(files, tmp_path / "merged.pdb")
+    assert (tmp_path / "merged.pdb").read_text() == want
+    rng = np.random.default_rng(3)                       # the pLDDT values oracle.make_golden_merge.inputs drew
+    pl = []
+    for n in range(3):
+        rng.standard_normal((5, 3, 3)); rng.standard_normal((5, 3))
+        pl.append(rng.random(5).astype(np.float32))
+    assert pdb_models_text("ACD_K", np.stack(bbs), np.stack(oxs), np.stack(pl)) == want

@@ -117,7 +117,7 @@ def test_cli_end_to_end_with_deepspeed_checkpoint(tmp_path, capsys):
     files = list(out.glob("step6_eps1e-05_N5_*/bpti.pdb"))
     assert len(files) == 1
     pdb = files[0].read_text()
-    assert pdb.count("MODEL ") == 5 and pdb.count("ENDMDL") == 5 and pdb.rstrip().endswith("END")
+    assert pdb.count("MODEL ") == 5 and pdb.count("ENDMDL") == 6 and pdb.rstrip().endswith("END")
     assert all(len(ln) == 80 for ln in pdb.splitlines())
     atoms = [ln for ln in pdb.splitlines() if ln.startswith("ATOM")]
     assert len(atoms) == 5 * (58 * 4 - 1)                                              # no O on the last residue
