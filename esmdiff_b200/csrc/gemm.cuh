@@ -566,6 +566,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     if (rot && mt != rope_mt) {
 #endif
                         const int row = row_base + lane < p.M ? row_base + lane : p.M - 1;
+#ifndef ESMDIFF_ROPE_TABLE
+                        // the rotary factors of this thread's token position from MUFU sin / cos (the special-function
+                        // unit is idle in a GEMM) instead of a 256-byte table row per thread and tile through L1, which
+                        // competes with the operand traffic of the main loop: 242.7 -> 230.4 us at M = 25 800
+                        // (profiles/r4c_qkv_rope_on_the_fly.txt; -DESMDIFF_ROPE_TABLE builds the table form).
+                        // sin.approx / cos.approx reduce the argument in fp32: <= ~1e-4 absolute at position 1026
+                        // -- the reference's own fp32 angle t * inv_freq is only good to 6e-5 there, and both are
+                        // 40x below the bf16 rounding of the rotated q', k'.
+                        const float INV_FREQ[32] = {1.000000000e+00f, 7.498942018e-01f, 5.623413324e-01f, 4.216965139e-01f, 3.162277639e-01f, 2.371373922e-01f, 1.778279394e-01f, 1.333521456e-01f, 1.000000015e-01f, 7.498941571e-02f, 5.623412877e-02f, 4.216964915e-02f, 3.162277862e-02f, 2.371373586e-02f, 1.778279431e-02f, 1.333521493e-02f, 9.999999776e-03f, 7.498942316e-03f, 5.623413250e-03f, 4.216964822e-03f, 3.162277862e-03f, 2.371373819e-03f, 1.778279431e-03f, 1.333521446e-03f, 1.000000047e-03f, 7.498941850e-04f, 5.623413017e-04f, 4.216965463e-04f, 3.162277862e-04f, 2.371373848e-04f, 1.778279402e-04f, 1.333521504e-04f};
+                        const float fp = static_cast<float>(row % p.T);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) __sincosf(fp * INV_FREQ[i], &rsin[i], &rcos[i]);
+#else
                         const float4* rp = reinterpret_cast<const float4*>(p.rope + static_cast<long long>(row % p.T) * 64);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -573,6 +586,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                             rcos[4 * i] = c4.x; rcos[4 * i + 1] = c4.y; rcos[4 * i + 2] = c4.z; rcos[4 * i + 3] = c4.w;
                             rsin[4 * i] = s4.x; rsin[4 * i + 1] = s4.y; rsin[4 * i + 2] = s4.z; rsin[4 * i + 3] = s4.w;
                         }
+#endif
                         rope_mt = mt;
                     }
                 } else {
