@@ -91,10 +91,18 @@ template <int EPI, int BN> struct Cfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int BOXES = (EPI == EPI_RESID_F32 || EPI == EPI_RESID_F32_LN) ? 0 : 1;    // the residual epilogue stages nothing
     // EPI_QKV_ROPE_LN: per epilogue warp, the three per-column vectors (colsum, bias, q/k gamma) of its
-    // 128 columns, fetched once per tile while the main loop runs and then read as shared-memory
-    // broadcasts (ncu r2c: as direct global loads right before their use they cost the epilogue an
-    // exposed L2 round trip per 16 columns -- 7.2k of 13.8k stall samples -- and the tensor pipe 15 points)
+    // 128 columns are fetched once per tile while the main loop runs (ncu r2c: as direct global loads
+    // right before their use they cost the epilogue an exposed L2 round trip per 16 columns -- 7.2k of
+    // 13.8k stall samples -- and the tensor pipe 15 points).  They are held as one float4 per lane and
+    // broadcast with shuffles; the first form staged them in shared memory (-DESMDIFF_VEC_SMEM): 12 KiB
+    // that cost the TMA ring its sixth stage, and 96 broadcast LDS.128 per thread and tile next to a main
+    // loop that already saturates the shared-memory port -- 232.4 vs 226.3 us at M = 25 800
+    // (profiles/r4e_qkv_vectors_by_shuffle.txt)
+#ifndef ESMDIFF_VEC_SMEM                                     // the three vectors live in registers, one float4 per lane (below)
+    static constexpr int VEC_BYTES = 0;
+#else
     static constexpr int VEC_BYTES = EPI == EPI_QKV_ROPE_LN ? 3 * 128 * 4 : 0;
+#endif
     static constexpr int STG_BYTES = EPI_WARPS * (BOXES * BOX_BYTES + VEC_BYTES);
     static constexpr int STAGES_FIT = (227 * 1024 - 1024 - 512 - STG_BYTES) / STAGE_BYTES;
 #ifdef ESMDIFF_STAGES_CAP                                   // experiment builds: cap the TMA ring depth (tools/kbench_qkv_variants.py)
@@ -535,6 +543,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                 // while the main loop of this tile is still running
                 float rstd, nrm;
                 bool rot = false;
+#ifndef ESMDIFF_VEC_SMEM
+                float4 vc4 = make_float4(0.f, 0.f, 0.f, 0.f), vb4 = vc4, vg4 = vc4;
+                // 16 consecutive entries of a vector held as one float4 per lane: lanes base .. base + 3
+                auto bcast16 = [&](float* r, const float4& v, int base) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        r[4 * j] = __shfl_sync(0xffffffffu, v.x, base + j);
+                        r[4 * j + 1] = __shfl_sync(0xffffffffu, v.y, base + j);
+                        r[4 * j + 2] = __shfl_sync(0xffffffffu, v.z, base + j);
+                        r[4 * j + 3] = __shfl_sync(0xffffffffu, v.w, base + j);
+                    }
+                };
+#endif
                 if constexpr (ROPE) {
                     // contiguous tile ranges: consecutive tiles share their rows, so the row statistics
                     // and the rotary table row are fetched once per row tile
@@ -549,6 +570,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                     nrm = nrm_c;
                     // this warp's 128 columns of colsum / bias / gamma -> shared memory (latency hidden
                     // behind the wait for the accumulators)
+#ifndef ESMDIFF_VEC_SMEM
+                    vc4 = __ldg(reinterpret_cast<const float4*>(p.colsum + n0) + lane);
+                    vb4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + lane);
+                    vg4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (rot) vg4 = __ldg(reinterpret_cast<const float4*>(p.qk_gamma + n0) + lane);
+#else
                     __syncwarp();
                     {
                         const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.colsum + n0) + lane);
@@ -560,6 +587,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                         reinterpret_cast<float4*>(vec + 256)[lane] = g4;
                     }
                     __syncwarp();
+#endif
 #ifdef ESMDIFF_EXP_NOTABLE                                  // timing experiment: no rotary table loads (results wrong)
                     if (rot && rope_mt < 0) {
 #else
@@ -608,8 +636,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                                 uint32_t v[16];
                                 float cs[16], bs[16];
                                 tmem_ld_32x32b_x16(t_row + c * 64 + hh * 16, v);
+#ifndef ESMDIFF_VEC_SMEM
+                                bcast16(cs, vc4, c * 16 + hh * 4);
+                                bcast16(bs, vb4, c * 16 + hh * 4);
+#else
                                 ld_uniform_smem<16>(cs, vec + c * 64 + hh * 16);
                                 ld_uniform_smem<16>(bs, vec + 128 + c * 64 + hh * 16);
+#endif
                                 tmem_ld_wait();
                                 float y[16];
 #pragma unroll
@@ -663,9 +696,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA,     // A   [M, K] b
                             float cs[16], bs[16], gs[16];
                             const int vo = c * 64 + hq * 16;
                             tmem_ld_32x32b_x16(t_row + vo, v);
+#ifndef ESMDIFF_VEC_SMEM
+                            bcast16(cs, vc4, vo >> 2);
+                            bcast16(bs, vb4, vo >> 2);
+                            bcast16(gs, vg4, vo >> 2);
+#else
                             ld_uniform_smem<16>(cs, vec + vo);
                             ld_uniform_smem<16>(bs, vec + 128 + vo);
                             ld_uniform_smem<16>(gs, vec + 256 + vo);
+#endif
                             tmem_ld_wait();
                             uint32_t o[8];
 #pragma unroll
